@@ -1,0 +1,141 @@
+/* sgam_b200.h -- C ABI of libsgam_b200.so: the B200 (sm_100a) kernels behind the SGAM per-frame hot path.
+ *
+ * The reference (yshen47/SGAM_NeurIPS22 @ 780feff) is pure PyTorch and has no FFI of its own; each
+ * entry point below replaces the ATen call sequence of one reference function (cited as
+ * file:line relative to the reference root) and is bound from Python with ctypes
+ * (sgam_neurips22_b200/_lib.py; the reference-side stub is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (PyTorch tensors) unless named host_*;
+ *     the library never allocates, frees or keeps a pointer past the call;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no synchronisation), so they
+ *     can be captured into a CUDA graph;
+ *   - return 0 on success, a negative sgam_status on failure; sgam_last_error() gives the message of the
+ *     last failure on the calling thread; nothing throws;
+ *   - fp32 everywhere unless stated; "NHWC" = [B,H,W,C] contiguous, "NCHW" = [B,C,H,W] contiguous;
+ *   - re-entrant per stream: one process per GPU (or several threads with distinct streams and buffers).
+ */
+#ifndef SGAM_B200_H
+#define SGAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SGAM_OK = 0,
+    SGAM_ERR_INVALID = -1,     /* bad shape / null pointer / unsupported flag combination */
+    SGAM_ERR_CUDA = -2,        /* a CUDA runtime call or kernel launch failed */
+    SGAM_ERR_UNSUPPORTED = -3  /* valid request the library has no kernel for */
+} sgam_status;
+
+enum { SGAM_DATASET_CLEVR = 0, SGAM_DATASET_GOOGLE_EARTH = 1 };
+enum { SGAM_SPLAT_LAST_WRITER = 0,   /* reference order: last point in (pixel-major, source-minor) order wins */
+       SGAM_SPLAT_ZMIN = 1 };        /* nearest depth wins (atomic-min z-buffer); flagged deviation */
+
+const char *sgam_last_error(void);
+int sgam_version(void);              /* 10000*major + 100*minor + patch */
+int sgam_sm_count(int device);       /* multiprocessors of `device` (148 on B200), <0 on error */
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage (i): forward splat.  Replaces sgam/point_rendering/warp.py:193-286
+ * render_projection_from_srcs_fast (pixel2cam :28-40, rigid transform :215, projection :222-225,
+ * index_put_ scatter :251,261, per-channel 3x3 median hole fill :271-279 via median_blur :289-347,
+ * hole mask :285) fused with VQModel.get_x's inverse-depth coding (sgam/generative_sensing_module/
+ * model.py:210-229,237).
+ *
+ *   src_rgb    [B,N,*]  source colours; element (b,n,c,pixel p) at ((b*N+n)*3*H*W + c*rgb_cs + p*rgb_ps):
+ *              rgb_cs=H*W, rgb_ps=1 for [B,N,3,H,W]; rgb_cs=1, rgb_ps=3 for the batch's native [B,N,H,W,3]
+ *   src_depth  [B,N,H,W]
+ *   K_tgt      [B,3,3]   target intrinsics            Kinv_src [B*N,3,3] inverse source intrinsics
+ *   T_src2tgt  [B*N,4,4] row-major rigid transforms (model.py:188-195)
+ *   winner     [B,H,W] u64 workspace (sgam_splat_workspace_bytes); on return holds the per-pixel winner
+ *              key: 0 = no point; low 32 bits = 1 + (p*N + n) of the winning source point
+ *   x          [B,4,H,W] out: filled rgb (3) + inverse-depth code (holes = -2)      (model.py:237)
+ *   mask       [B,H,W] u8 out: extrapolation mask (merged depth <= 0)                 (warp.py:285)
+ *   merge_depth[B,H,W] out or NULL: filled metric depth                              (warp.py:279)
+ *   proj       [B,4,H,W] out or NULL: scattered, unfilled rgb + depth                 (warp.py:251,261)
+ *   inbounds   [B,H*W*N] u8 out or NULL: warp.py:232 bounds mask in (pixel, source) order
+ */
+size_t sgam_splat_workspace_bytes(int B, int H, int W);
+int sgam_splat_forward(const float *src_rgb, long long rgb_cs, long long rgb_ps, const float *src_depth,
+                       const float *K_tgt, const float *Kinv_src, const float *T_src2tgt,
+                       int B, int N, int H, int W, int policy, int dataset,
+                       void *winner, float *x, uint8_t *mask, float *merge_depth, float *proj,
+                       uint8_t *inbounds, void *stream);
+
+/* 3x3 zero-padded lower median per plane.  Replaces warp.py:289-347 median_blur(input,(3,3)). */
+int sgam_median_blur3(const float *in, float *out, int planes, int H, int W, void *stream);
+
+/* get_x for a pre-warped input (use_rgbd_integration=True): model.py:196-199,210-229,237.
+ *   rgb [B,3,H,W], depth [B,H,W] -> x [B,4,H,W], mask [B,H,W] u8 (depth <= 0) */
+int sgam_depth_code(const float *rgb, const float *depth, int B, int H, int W, int dataset,
+                    float *x, uint8_t *mask, void *stream);
+
+/* Backward warp + per-pixel source selection.  Replaces sgam/inference_pipeline.py:662-743
+ * InfiniteSceneGeneration.inverse_warping (pixel2cam :619-632, cam2pixel :634-660, nearest
+ * grid_sample :707, depth-residual z-test loop :725-737).
+ *   src_rgb as in sgam_splat_forward; src_depth [B,N,H,W]; tgt_depth [B,H,W]; Kinv_tgt [B,3,3];
+ *   proj [B*N,3,4] = K_src @ T_tgt2src[:3] (host-side 3x4 product, :696)
+ *   out [B,3,H,W] (0 where no source is valid); best_src [B,H,W] i32 or NULL (-1 = none) */
+int sgam_inverse_warp(const float *src_rgb, long long rgb_cs, long long rgb_ps, const float *src_depth,
+                      const float *tgt_depth, const float *Kinv_tgt, const float *proj,
+                      int B, int N, int H, int W, float *out, int32_t *best_src, void *stream);
+
+/* Per-frame output conversion.  Replaces inference_pipeline.py:893-911.
+ *   dec [B,4,H,W] -> rgb_u8 [B,H,W,3] (clip((x+1)/2*255) truncated), depth [B,H,W] metric */
+int sgam_frame_outputs(const float *dec, int B, int H, int W, int dataset, uint8_t *rgb_u8, float *depth,
+                       void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage (ii): codebook nearest neighbour.  Replaces sgam/generative_sensing_module/modules/vqvae/
+ * quantize.py:275-319 VectorQuantizer2.forward and :344-381 get_multiple_codewords(topk=1):
+ * d = (|z|^2 + |e|^2) - 2 z.e, arg-min with first-index ties, z_q = E[idx].
+ *   z [T,D] token-major (= NHWC latent), codebook [n_e,D], best [T] u64 workspace,
+ *   idx [T] i64 out, z_q [T,D] out, dmin [T] out or NULL.  D % 32 == 0, n_e % 128 == 0.
+ */
+size_t sgam_vq_workspace_bytes(int T);
+int sgam_vq_nearest(const float *z, const float *codebook, int T, int n_e, int D, void *best,
+                    int64_t *idx, float *z_q, float *dmin, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage (iii): VQGAN encoder / decoder operators (sgam/generative_sensing_module/modules/
+ * diffusionmodules/model.py).  Activations are NHWC inside the network.
+ */
+
+/* VQModel.encode stem: cat(x, mask) -> 1x1 conv 5->4 (model.py:106-113, conv_in :54).
+ *   x [B,4,H,W] NCHW, mask [B,H,W] u8 or NULL (zeros), w [4,5], bias [4] -> y [B,H,W,4] NHWC */
+int sgam_stem_conv(const float *x, const uint8_t *mask, const float *w, const float *bias,
+                   int B, int H, int W, float *y, void *stream);
+
+/* Conv2d 3x3 / 1x1 as implicit GEMM (model.py:43,62-72,88-117; Downsample :56-75; Upsample :38-53).
+ *   x [B,H,W,Cin]; w [Cout, k*k*Cin] with K index (kh*k+kw)*Cin+ci (OIHW repacked once by the host);
+ *   bias [Cout]; residual [B,Ho,Wo,Cout] or NULL (added in the epilogue); y [B,Ho,Wo,Cout]
+ *   ksize 1|3; stride 1|2; pad_mode 0 = symmetric k/2, 1 = right/bottom only (Downsample: pad (0,1,0,1),
+ *   stride 2); upsample 1 = the input is read through a nearest x2 up-sampling (Upsample fused).
+ *   out_nchw 1 = write y as [B,Cout,Ho,Wo] (decoder conv_out). */
+int sgam_conv2d(const float *x, const float *w, const float *bias, const float *residual, float *y,
+                int B, int H, int W, int Cin, int Cout, int ksize, int stride, int pad_mode,
+                int upsample, int out_nchw, void *stream);
+
+/* GroupNorm(32, C, eps=1e-6) (+ swish) (model.py:29-35).  Two launches: statistics, then apply.
+ *   x [B,HW,C]; partial [B,S,32,2] f64 workspace (S = sgam_gn_splits(HW)); y [B,HW,C] */
+int sgam_gn_splits(long long HW);
+int sgam_groupnorm(const float *x, const float *gamma, const float *beta, float *y, double *partial,
+                   int B, long long HW, int C, int swish, void *stream);
+
+/* Batched C = alpha * A . B^T (+ bias_m[row]) : A [batch,M,K], B [batch,N,K], C [batch,M,N]; strides in
+ * elements; used for the attention score / value products and V^T = W_v . h^T (model.py:168-190). */
+int sgam_gemm_nt(const float *A, const float *Bm, float *C, const float *bias_m, int batch, int M, int N,
+                 int K, long long sA, long long sB, long long sC, float alpha, void *stream);
+
+/* Row softmax in place: x [rows, cols] (model.py:181). */
+int sgam_softmax_rows(float *x, long long rows, int cols, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGAM_B200_H */

@@ -1,0 +1,63 @@
+"""ctypes binding of libsgam_b200.so (include/sgam_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import of any product op raises, and every
+op checks its status code and raises RuntimeError(sgam_last_error()).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsgam_b200.so")
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_f = ctypes.c_float
+c_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/sgam_b200.h one to one (tests/test_abi.py checks the header)
+SIGNATURES = {
+    "sgam_last_error": (ctypes.c_char_p, []),
+    "sgam_version": (c_i, []),
+    "sgam_sm_count": (c_i, [c_i]),
+    "sgam_splat_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
+    "sgam_splat_forward": (c_i, [c_p, c_ll, c_ll, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i,
+                                 c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "sgam_median_blur3": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
+    "sgam_depth_code": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "sgam_inverse_warp": (c_i, [c_p, c_ll, c_ll, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "sgam_frame_outputs": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "sgam_vq_workspace_bytes": (c_sz, [c_i]),
+    "sgam_vq_nearest": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "sgam_stem_conv": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "sgam_conv2d": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sgam_gn_splits": (c_i, [c_ll]),
+    "sgam_groupnorm": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p]),
+    "sgam_gemm_nt": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_f, c_p]),
+    "sgam_softmax_rows": (c_i, [c_p, c_ll, c_i, c_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every prototype.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m sgam_neurips22_b200.build` "
+                "(there is no CPU fallback for the SGAM hot path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError = header / library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().sgam_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed with status {status}: {msg}")

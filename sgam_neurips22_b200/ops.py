@@ -1,0 +1,230 @@
+"""Tensor-level wrappers over the C ABI (include/sgam_b200.h).
+
+PyTorch is plumbing here: it owns the device memory and the stream; every function below checks its inputs,
+allocates the outputs and enqueues the library's kernels on `torch.cuda.current_stream()`.  Nothing falls
+back to ATen: a missing library or a CPU tensor raises.
+"""
+import torch
+
+from . import _lib
+
+DATASET_ID = {"clevr-infinite": 0, "google_earth": 1}
+SPLAT_LAST_WRITER, SPLAT_ZMIN = 0, 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype=torch.float32, name="tensor"):
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the SGAM hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def dataset_id(dataset):
+    if dataset not in DATASET_ID:
+        raise NotImplementedError(dataset)        # same error the reference raises (model.py:230-231)
+    return DATASET_ID[dataset]
+
+
+# ---------------------------------------------------------------------------------------------- stage (i)
+def splat_forward(src_rgb, src_depth, K_tgt, Kinv_src, T_src2tgt, dataset, channels_last=False,
+                  policy=SPLAT_LAST_WRITER, want_merge_depth=False, want_proj=False, want_inbounds=False,
+                  workspace=None):
+    """Fused forward splat + hole fill + mask + inverse-depth code (warp.py:193-286, model.py:210-237).
+
+    src_rgb [B,N,3,H,W] (or [B,N,H,W,3] with channels_last), src_depth [B,N,H,W], K_tgt [B,3,3],
+    Kinv_src [B,N,3,3], T_src2tgt [B,N,4,4].  Returns dict(x, mask, merge_depth?, proj?, inbounds?, winner)."""
+    lib = _lib.load()
+    B, N, H, W = src_depth.shape
+    _chk(src_rgb, name="src_rgb"), _chk(src_depth, name="src_depth"), _chk(K_tgt, name="K_tgt")
+    _chk(Kinv_src, name="Kinv_src"), _chk(T_src2tgt, name="T_src2tgt")
+    exp = (B, N, H, W, 3) if channels_last else (B, N, 3, H, W)
+    if tuple(src_rgb.shape) != exp or tuple(K_tgt.shape) != (B, 3, 3) or Kinv_src.numel() != B * N * 9 \
+            or T_src2tgt.numel() != B * N * 16:
+        raise RuntimeError(f"splat_forward: inconsistent shapes {tuple(src_rgb.shape)} {tuple(src_depth.shape)}")
+    cs, ps = (1, 3) if channels_last else (H * W, 1)
+    dev = src_depth.device
+    if workspace is None:
+        workspace = torch.empty(lib.sgam_splat_workspace_bytes(B, H, W) // 8, dtype=torch.int64, device=dev)
+    x = torch.empty(B, 4, H, W, device=dev)
+    mask = torch.empty(B, 1, H, W, dtype=torch.uint8, device=dev)
+    md = torch.empty(B, 1, H, W, device=dev) if want_merge_depth else None
+    proj = torch.empty(B, 4, H, W, device=dev) if want_proj else None
+    inb = torch.empty(B, H * W * N, dtype=torch.uint8, device=dev) if want_inbounds else None
+    _lib.check(lib.sgam_splat_forward(src_rgb.data_ptr(), cs, ps, src_depth.data_ptr(), K_tgt.data_ptr(),
+                                      Kinv_src.data_ptr(), T_src2tgt.data_ptr(), B, N, H, W, policy,
+                                      dataset_id(dataset), workspace.data_ptr(), x.data_ptr(), mask.data_ptr(),
+                                      _ptr(md), _ptr(proj), _ptr(inb), _stream()), "sgam_splat_forward")
+    return dict(x=x, mask=mask, merge_depth=md, proj=proj, inbounds=inb, winner=workspace)
+
+
+def median_blur3(x):
+    """3x3 zero-padded median per plane (warp.py:289-347)."""
+    lib = _lib.load()
+    _chk(x, name="input")
+    if x.dim() != 4:
+        raise ValueError(f"Invalid input shape, we expect BxCxHxW. Got: {x.shape}")   # warp.py:326-327
+    out = torch.empty_like(x)
+    H, W = x.shape[-2:]
+    _lib.check(lib.sgam_median_blur3(x.data_ptr(), out.data_ptr(), x.numel() // (H * W), H, W, _stream()),
+               "sgam_median_blur3")
+    return out
+
+
+def depth_code(rgb, depth, dataset):
+    """get_x on a pre-warped input (model.py:196-199, 210-237): rgb [B,3,H,W], depth [B,H,W] -> x, mask."""
+    lib = _lib.load()
+    _chk(rgb, name="rgb"), _chk(depth, name="depth")
+    B, _, H, W = rgb.shape
+    x = torch.empty(B, 4, H, W, device=rgb.device)
+    mask = torch.empty(B, 1, H, W, dtype=torch.uint8, device=rgb.device)
+    _lib.check(lib.sgam_depth_code(rgb.data_ptr(), depth.data_ptr(), B, H, W, dataset_id(dataset), x.data_ptr(),
+                                   mask.data_ptr(), _stream()), "sgam_depth_code")
+    return x, mask
+
+
+def inverse_warp(src_rgb, src_depth, tgt_depth, Kinv_tgt, proj, channels_last=False, want_best=False):
+    """inference_pipeline.py:662-743.  src_rgb [B,N,3,H,W], src_depth [B,N,H,W], tgt_depth [B,H,W],
+    Kinv_tgt [B,3,3], proj [B,N,3,4] -> warped [B,3,H,W] (and best_src [B,H,W] int32)."""
+    lib = _lib.load()
+    for n, t in (("src_rgb", src_rgb), ("src_depth", src_depth), ("tgt_depth", tgt_depth), ("Kinv_tgt", Kinv_tgt),
+                 ("proj", proj)):
+        _chk(t, name=n)
+    B, N, H, W = src_depth.shape
+    cs, ps = (1, 3) if channels_last else (H * W, 1)
+    out = torch.empty(B, 3, H, W, device=src_depth.device)
+    best = torch.empty(B, H, W, dtype=torch.int32, device=src_depth.device) if want_best else None
+    _lib.check(lib.sgam_inverse_warp(src_rgb.data_ptr(), cs, ps, src_depth.data_ptr(), tgt_depth.data_ptr(),
+                                     Kinv_tgt.data_ptr(), proj.data_ptr(), B, N, H, W, out.data_ptr(), _ptr(best),
+                                     _stream()), "sgam_inverse_warp")
+    return (out, best) if want_best else out
+
+
+def frame_outputs(dec, dataset, rgb_u8=None, depth=None):
+    """inference_pipeline.py:893-911: dec [B,4,H,W] -> uint8 RGB [B,H,W,3], metric depth [B,H,W]."""
+    lib = _lib.load()
+    _chk(dec, name="dec")
+    B, C, H, W = dec.shape
+    if C != 4:
+        raise RuntimeError("frame_outputs: dec must be [B,4,H,W]")
+    if rgb_u8 is None:
+        rgb_u8 = torch.empty(B, H, W, 3, dtype=torch.uint8, device=dec.device)
+    if depth is None:
+        depth = torch.empty(B, H, W, device=dec.device)
+    _lib.check(lib.sgam_frame_outputs(dec.data_ptr(), B, H, W, dataset_id(dataset), rgb_u8.data_ptr(),
+                                      depth.data_ptr(), _stream()), "sgam_frame_outputs")
+    return rgb_u8, depth
+
+
+# --------------------------------------------------------------------------------------------- stage (ii)
+def vq_nearest(z_tokens, codebook, want_dmin=False, workspace=None):
+    """z_tokens [T,D] (NHWC latent flattened), codebook [n_e,D] -> idx [T] int64, z_q [T,D] (, dmin [T])."""
+    lib = _lib.load()
+    _chk(z_tokens, name="z"), _chk(codebook, name="codebook")
+    T, D = z_tokens.shape
+    dev = z_tokens.device
+    if workspace is None:
+        workspace = torch.empty(T, dtype=torch.int64, device=dev)
+    idx = torch.empty(T, dtype=torch.int64, device=dev)
+    z_q = torch.empty(T, D, device=dev)
+    dmin = torch.empty(T, device=dev) if want_dmin else None
+    _lib.check(lib.sgam_vq_nearest(z_tokens.data_ptr(), codebook.data_ptr(), T, codebook.shape[0], D,
+                                   workspace.data_ptr(), idx.data_ptr(), z_q.data_ptr(), _ptr(dmin), _stream()),
+               "sgam_vq_nearest")
+    return (idx, z_q, dmin) if want_dmin else (idx, z_q)
+
+
+# -------------------------------------------------------------------------------------------- stage (iii)
+def stem_conv(x, mask, w, bias):
+    """cat(x, mask) -> 1x1 conv 5->4 (model.py:106-113).  x [B,4,H,W] NCHW -> [B,H,W,4] NHWC."""
+    lib = _lib.load()
+    _chk(x, name="x"), _chk(w, name="w"), _chk(bias, name="bias")
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    B, _, H, W = x.shape
+    y = torch.empty(B, H, W, 4, device=x.device)
+    _lib.check(lib.sgam_stem_conv(x.data_ptr(), _ptr(mask), w.data_ptr(), bias.data_ptr(), B, H, W, y.data_ptr(),
+                                  _stream()), "sgam_stem_conv")
+    return y
+
+
+def conv_out_hw(H, W, ksize, stride, pad_mode, upsample):
+    Hl, Wl = H << upsample, W << upsample
+    if pad_mode == 0:
+        p = ksize // 2
+        return (Hl + 2 * p - ksize) // stride + 1, (Wl + 2 * p - ksize) // stride + 1
+    return (Hl + 1 - ksize) // stride + 1, (Wl + 1 - ksize) // stride + 1
+
+
+def conv2d(x, w, bias, residual=None, ksize=3, stride=1, pad_mode=0, upsample=0, out_nchw=False, out=None):
+    """x [B,H,W,Cin] NHWC, w [Cout, k*k*Cin] (K-major), bias [Cout] -> [B,Ho,Wo,Cout] (or NCHW for the head)."""
+    lib = _lib.load()
+    _chk(x, name="x"), _chk(w, name="w"), _chk(bias, name="bias")
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    if w.shape[1] != ksize * ksize * Cin:
+        raise RuntimeError(f"conv2d: weight {tuple(w.shape)} does not match k={ksize} Cin={Cin}")
+    Ho, Wo = conv_out_hw(H, W, ksize, stride, pad_mode, upsample)
+    if out is None:
+        out = torch.empty((B, Cout, Ho, Wo) if out_nchw else (B, Ho, Wo, Cout), device=x.device)
+    if residual is not None:
+        _chk(residual, name="residual")
+    _lib.check(lib.sgam_conv2d(x.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(residual), out.data_ptr(), B, H, W,
+                               Cin, Cout, ksize, stride, pad_mode, upsample, int(out_nchw), _stream()), "sgam_conv2d")
+    return out
+
+
+def groupnorm(x, gamma, beta, swish, out=None, workspace=None):
+    """GroupNorm(32, C, eps=1e-6) (+ swish) on NHWC x [B,H,W,C] (model.py:29-35)."""
+    lib = _lib.load()
+    _chk(x, name="x"), _chk(gamma, name="gamma"), _chk(beta, name="beta")
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    S = lib.sgam_gn_splits(HW)
+    if workspace is None:
+        workspace = torch.empty(B * S * 64, dtype=torch.float64, device=x.device)
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(lib.sgam_groupnorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                  workspace.data_ptr(), B, HW, C, int(swish), _stream()), "sgam_groupnorm")
+    return out
+
+
+def gemm_nt(A, Bm, bias_m=None, alpha=1.0, out=None):
+    """C = alpha * A . B^T (+ bias_m per row).  A [batch,M,K] or [M,K]; B [batch,N,K] or [N,K]."""
+    lib = _lib.load()
+    _chk(A, name="A"), _chk(Bm, name="B")
+    squeeze = A.dim() == 2 and Bm.dim() == 2
+    A3 = A.unsqueeze(0) if A.dim() == 2 else A
+    B3 = Bm.unsqueeze(0) if Bm.dim() == 2 else Bm
+    batch = max(A3.shape[0], B3.shape[0])
+    _, M, K = A3.shape
+    N = B3.shape[1]
+    if B3.shape[2] != K or A3.shape[0] not in (1, batch) or B3.shape[0] not in (1, batch):
+        raise RuntimeError(f"gemm_nt: shapes {tuple(A.shape)} x {tuple(Bm.shape)}")
+    sA = M * K if A3.shape[0] == batch else 0          # a 2-D operand is shared by every batch element
+    sB = N * K if B3.shape[0] == batch else 0
+    if out is None:
+        out = torch.empty(batch, M, N, device=A.device)
+    _lib.check(lib.sgam_gemm_nt(A3.data_ptr(), B3.data_ptr(), out.data_ptr(), _ptr(bias_m), batch, M, N, K,
+                                sA, sB, M * N, float(alpha), _stream()), "sgam_gemm_nt")
+    return out[0] if squeeze and out.dim() == 3 else out
+
+
+def softmax_rows_(x):
+    """In-place softmax over the last dimension (model.py:181)."""
+    lib = _lib.load()
+    _chk(x, name="x")
+    cols = x.shape[-1]
+    _lib.check(lib.sgam_softmax_rows(x.data_ptr(), x.numel() // cols, cols, _stream()), "sgam_softmax_rows")
+    return x
