@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- novel-view RGB-D frames/sec of the SGAM scene-generation step on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                      # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1      # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                          # N ranks, weak scaling
+
+One step = one pass of the hot path (forward splat + hole fill + depth code -> VQGAN encode -> codebook arg-min ->
+decode -> uint8 / metric-depth conversion) over `--batch` independent trajectories' frames of synthetic 256x256
+RGB-D (BASELINE.json configs[1], CLEVR-Infinite; `--dataset google_earth` gives the configs[2]-shaped step).
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "novel-view RGB-D frames/sec @256x256"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    tflops_burst=p["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def time_steps(fn, steps, world):
+    """barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_fps(state_dict, batch_np, dataset, min_seconds, max_frames):
+    """The reference's CPU path (oracle port: same ATen fp32 operators, all host threads) on a bounded sample."""
+    from oracle import model as omodel
+    from oracle import native
+    native.build()
+    torch.set_num_threads(os.cpu_count())
+    sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    one = {k: v[:1] for k, v in batch_np.items()}
+    omodel.scene_step(sd, one, dataset)                                   # warm-up (1 frame)
+    n, t0 = 0, time.perf_counter()
+    while n < max_frames and (n == 0 or time.perf_counter() - t0 < min_seconds):
+        omodel.scene_step(sd, one, dataset)
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from sgam_neurips22_b200 import synthetic
+    from sgam_neurips22_b200.model import VQModel
+    model = synthetic.randomize_weights(VQModel(**synthetic.model_kwargs(args.dataset)), seed=0)
+    batch_np = synthetic.scene_step_batch(args.dataset, res=args.res, batch=1, seed=100)
+    from oracle import model as omodel
+    from oracle import native
+    native.build()
+    torch.set_num_threads(os.cpu_count())
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    for _ in range(args.warmup):
+        omodel.scene_step(sd, batch_np, args.dataset)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        omodel.scene_step(sd, batch_np, args.dataset)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    cfg = workload_config(args, 1)
+    cfg["frames_per_step"] = 1
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{args.steps} frames, batch 1 (the reference hard-codes batch 1), torch CPU fp32 oracle port "
+                                   "of get_x + VQModel.forward(topk=1) + uint8/depth conversion"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, world):
+    name = "CLEVR-Infinite" if args.dataset == "clevr-infinite" else "GoogleEarth-Infinite"
+    return {"workload": f"{name} {args.res}x{args.res} full scene-gen step (forward splat + VQGAN encode + VQ arg-min + decode), "
+                        f"{args.batch} independent trajectories per GPU",
+            "dataset": args.dataset, "resolution": args.res, "trajectories_per_gpu": args.batch,
+            "frames_per_step": args.batch * world, "parallelism": f"dp{world} (trajectory sharding, no collective in the loop)",
+            "weights": "random init (no checkpoint ships with the reference), N(0,1) codebook",
+            "l2": "per-step working set (271 MB fp32 weights + >1 GB activations per frame) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dataset", default="clevr-infinite", choices=["clevr-infinite", "google_earth"])
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=8, help="independent trajectories per GPU (BASELINE.json configs[3]: 64 over 8 GPUs)")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the SGAM hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    from sgam_neurips22_b200 import _lib, ops, synthetic
+    from sgam_neurips22_b200 import dist as sdist
+    from sgam_neurips22_b200.model import VQModel
+    lib = _lib.load()
+    peaks = load_peaks()
+    ds, B, res = args.dataset, args.batch, args.res
+
+    model = synthetic.randomize_weights(VQModel(**synthetic.model_kwargs(ds)), seed=0).to(dev).eval()
+    eng = model.engine
+    batch_np = synthetic.scene_step_batch(ds, res=res, batch=B, seed=100 + rank)
+    N = batch_np["src_depths"].shape[1]
+
+    # ---------------- device-resident leg (`value`) -----------------------------------------------------------
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in batch_np.items()}
+    r_rgb, r_dep = host["src_imgs"].to(dev), host["src_depths"].to(dev)
+    Kinv = model._kinv(host["Ks"])
+    K_tgt = host["Ks"][:, 0].contiguous().to(dev)
+    T = torch.eye(4).repeat(B, N, 1, 1)
+    T[..., :3, :3], T[..., :3, 3] = host["R_rels"], host["t_rels"]
+    T = T.to(dev)
+    ws = torch.empty(B * res * res, dtype=torch.int64, device=dev)
+    out_rgb = torch.empty(B, res, res, 3, dtype=torch.uint8, device=dev)
+    out_depth = torch.empty(B, res, res, device=dev)
+
+    def step_resident():
+        s = ops.splat_forward(r_rgb, r_dep, K_tgt, Kinv, T, ds, channels_last=True, workspace=ws)
+        dec, pre, zq, idx = eng.forward(s["x"], s["mask"])
+        ops.frame_outputs(dec, ds, rgb_u8=out_rgb, depth=out_depth)
+        return dec
+
+    c0 = lib.sgam_launch_count()
+    step_resident()
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.sgam_launch_count() - c0)
+
+    run_step = step_resident
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step_resident()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_resident()
+        run_step = graph.replay
+
+    for _ in range(args.warmup):
+        run_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = time_steps(run_step, args.steps, world)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    frames = B * world * args.steps
+    value = frames / (ms / 1000.0)
+
+    # ---------------- end-to-end leg (`e2e`): public API, host buffers, H2D + D2H inside the timed region --------
+    pin_rgb = torch.empty(B, res, res, 3, dtype=torch.uint8).pin_memory()
+    pin_depth = torch.empty(B, res, res).pin_memory()
+    api_batch = {k: host[k] for k in ("src_imgs", "src_depths", "Ks", "R_rels", "t_rels", "dst_img", "dst_depth")}
+    h2d = sum(api_batch[k].numel() * api_batch[k].element_size() for k in ("src_imgs", "src_depths", "Ks", "R_rels", "t_rels"))
+    d2h = pin_rgb.numel() + pin_depth.numel() * 4
+
+    def step_e2e():
+        b = dict(api_batch)
+        x, _, mask, _ = model.get_x(b, ds, return_extrapolation_mask=True, no_depth_range=True, parallel=True)
+        decs, _, pre, quants = model(x, topk=1, extrapolation_mask=mask, get_pre_quantized_feature=True,
+                                     get_quantized_feature=True, sample_number=1)
+        rgb, depth = ops.frame_outputs(decs[0][0], ds, rgb_u8=out_rgb, depth=out_depth)
+        pin_rgb.copy_(rgb, non_blocking=True)
+        pin_depth.copy_(depth, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                      # the caller reads the frame before the next step
+
+    for _ in range(args.warmup):
+        step_e2e()
+    e2e_steps = max(3, min(args.steps, 20))
+    ms_e2e = time_steps(step_e2e, e2e_steps, world)
+    e2e_value = B * world * e2e_steps / (ms_e2e / 1000.0)
+
+    # ---------------- roofline of the dominant kernel (conv implicit GEMM), measured live with CUDA events ------------
+    conv_events, orig_conv = [], ops.conv2d
+
+    def timed_conv(x, w, bias, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = orig_conv(x, w, bias, **kw)
+        e1.record()
+        m = y.numel() // w.shape[0]
+        conv_events.append((e0, e1, 2.0 * m * w.shape[0] * w.shape[1]))
+        return y
+
+    ops.conv2d = timed_conv
+    try:
+        for _ in range(2):
+            conv_events.clear()
+            step_resident()
+            torch.cuda.synchronize()
+    finally:
+        ops.conv2d = orig_conv
+    conv_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in conv_events)
+    conv_flops = sum(f for _, _, f in conv_events)
+    conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12
+    eager_ms = time_steps(step_resident, 3, 1)
+
+    def solo(fn, n=20):
+        for _ in range(3):
+            fn()
+        return time_steps(fn, n, 1) / n
+
+    splat_ms = solo(lambda: ops.splat_forward(r_rgb, r_dep, K_tgt, Kinv, T, ds, channels_last=True, workspace=ws))
+    splat_bytes = B * (N * res * res * 16 + res * res * 17)
+    pre = eng.encode(step_in_x := ops.splat_forward(r_rgb, r_dep, K_tgt, Kinv, T, ds, channels_last=True, workspace=ws)["x"], None)
+    vq_ms = solo(lambda: eng.quantize(pre))
+    Tk, D = pre.numel() // pre.shape[-1], pre.shape[-1]
+    vq_bytes = eng.n_embed * D * 4 + 2 * Tk * D * 4 + Tk * 8
+    vq_flops = 2.0 * Tk * eng.n_embed * D
+    del step_in_x
+
+    # ---------------- final map all-gather (the only collective; outside the frames/sec region) ----------------------
+    poses = torch.zeros(B, 12, dtype=torch.float64)
+    ag_ms = None
+    if world > 1:
+        sdist.gather_scene_map(out_rgb, out_depth, poses)
+        ag_ms = time_steps(lambda: sdist.gather_scene_map(out_rgb, out_depth, poses), 5, world) / 5
+
+    if rank == 0:
+        cfg = workload_config(args, world)
+        cfg["cuda_graph"] = graph is not None
+        cfg["sources_per_frame"] = int(N)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / e2e_steps, "api": "VQModel.get_x + VQModel.forward(topk=1) + frame_outputs, pinned host buffers"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"kernel": "conv2d implicit GEMM (sgam_conv2d)", "bound": "tensor", "achieved": conv_tflops,
+                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops"], "traffic": None,
+                         "peak_source": peaks["source"] + ", sustained bf16", "launches_per_step": len(conv_events),
+                         "share_of_step": conv_ms / eager_ms, "flops_per_step": conv_flops,
+                         "note": "fp32 CUDA-core implicit GEMM today; fraction is quoted against the tensor-pipe peak the "
+                                 "tcgen05 path is designed for"},
+            "kernels": {
+                "splat": {"bound": "hbm", "ms": splat_ms, "achieved": splat_bytes / (splat_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                          "unit": "GB/s", "frac": splat_bytes / (splat_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "bytes": splat_bytes},
+                "vq": {"bound": "hbm", "ms": vq_ms, "achieved": vq_bytes / (vq_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": vq_bytes / (vq_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "bytes": vq_bytes,
+                       "fp32_tflops": vq_flops / (vq_ms * 1e-3) / 1e12},
+                "step_eager_ms": eager_ms, "conv_ms": conv_ms},
+        }
+        if ag_ms is not None:
+            line["allgather_ms"] = ag_ms
+            line["allgather_bytes_per_rank"] = int(B * sdist.record_bytes(res, res))
+        if world == 1 and not args.no_cpu_baseline:
+            fps, n, dt = cpu_reference_fps(model.state_dict(), batch_np, ds, min_seconds=10.0, max_frames=8)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{n} frames of the same workload at batch 1 in {dt:.1f} s (torch CPU fp32 oracle port, "
+                                              f"{os.cpu_count()} threads; the reference hard-codes batch 1)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,7 @@ enum { SGAM_SPLAT_LAST_WRITER = 0,   /* reference order: last point in (pixel-ma
 const char *sgam_last_error(void);
 int sgam_version(void);              /* 10000*major + 100*minor + patch */
 int sgam_sm_count(int device);       /* multiprocessors of `device` (148 on B200), <0 on error */
+unsigned long long sgam_launch_count(void);   /* kernels this library has launched (or captured) so far in the process */
 
 /* ------------------------------------------------------------------------------------------------
  * Stage (i): forward splat.  Replaces sgam/point_rendering/warp.py:193-286
@@ -85,10 +86,13 @@ int sgam_inverse_warp(const float *src_rgb, long long rgb_cs, long long rgb_ps, 
                       const float *tgt_depth, const float *Kinv_tgt, const float *proj,
                       int B, int N, int H, int W, float *out, int32_t *best_src, void *stream);
 
-/* Per-frame output conversion.  Replaces inference_pipeline.py:893-911.
- *   dec [B,4,H,W] -> rgb_u8 [B,H,W,3] (clip((x+1)/2*255) truncated), depth [B,H,W] metric */
+/* Per-frame output conversion.  Replaces inference_pipeline.py:893-911 and, for the device-resident frame
+ * store, the PNG re-load of :534.
+ *   dec [B,4,H,W] -> rgb_u8 [B,H,W,3] (clip((x+1)/2*255) truncated), depth [B,H,W] metric,
+ *   src_rgb [B,H,W,3] or NULL: (float)(u8 / 127.5 - 1.0) evaluated in double, i.e. the fp32 source image a later
+ *   step would obtain by re-reading the saved PNG */
 int sgam_frame_outputs(const float *dec, int B, int H, int W, int dataset, uint8_t *rgb_u8, float *depth,
-                       void *stream);
+                       float *src_rgb, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage (ii): codebook nearest neighbour.  Replaces sgam/generative_sensing_module/modules/vqvae/

@@ -20,13 +20,14 @@ SIGNATURES = {
     "sgam_last_error": (ctypes.c_char_p, []),
     "sgam_version": (c_i, []),
     "sgam_sm_count": (c_i, [c_i]),
+    "sgam_launch_count": (ctypes.c_ulonglong, []),
     "sgam_splat_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "sgam_splat_forward": (c_i, [c_p, c_ll, c_ll, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i,
                                  c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "sgam_median_blur3": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "sgam_depth_code": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "sgam_inverse_warp": (c_i, [c_p, c_ll, c_ll, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
-    "sgam_frame_outputs": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "sgam_frame_outputs": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "sgam_vq_workspace_bytes": (c_sz, [c_i]),
     "sgam_vq_nearest": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "sgam_stem_conv": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),

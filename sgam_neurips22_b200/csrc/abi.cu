@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_sgam_launches = 0;
 
 void sgam_set_error(const char *fmt, ...) {
     va_list ap;
@@ -18,3 +19,4 @@ extern "C" int sgam_sm_count(int device) {
     SGAM_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
     return n;
 }
+extern "C" unsigned long long sgam_launch_count(void) { return g_sgam_launches; }

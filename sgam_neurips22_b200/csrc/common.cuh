@@ -24,7 +24,13 @@ void sgam_set_error(const char *fmt, ...);
         }                                                                             \
     } while (0)
 
-#define SGAM_LAUNCH_OK() SGAM_CUDA_OK(cudaGetLastError())
+// every kernel launch of the library goes through this macro: it also feeds sgam_launch_count()
+extern unsigned long long g_sgam_launches;
+#define SGAM_LAUNCH_OK()                  \
+    do {                                  \
+        ++g_sgam_launches;                \
+        SGAM_CUDA_OK(cudaGetLastError()); \
+    } while (0)
 
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 

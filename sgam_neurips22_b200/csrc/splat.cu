@@ -273,7 +273,7 @@ inverse_warp_kernel(const float *__restrict__ src_rgb, long long cs, long long p
 
 __global__ void __launch_bounds__(256)
 frame_outputs_kernel(const float *__restrict__ dec, int HW, int dataset, uint8_t *__restrict__ rgb,
-                     float *__restrict__ depth) {
+                     float *__restrict__ depth, float *__restrict__ src_rgb) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (p >= HW) return;
     const float *d = dec + (size_t)b * 4 * HW;
@@ -281,7 +281,9 @@ frame_outputs_kernel(const float *__restrict__ dec, int HW, int dataset, uint8_t
     for (int c = 0; c < 3; ++c) {                                       // inference_pipeline.py:898-901
         float v = __fmul_rn(__fdiv_rn(__fadd_rn(d[(size_t)c * HW + p], 1.0f), 2.0f), 255.0f);
         v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
-        rgb[((size_t)b * HW + p) * 3 + c] = (uint8_t)v;
+        const uint8_t u = (uint8_t)v;
+        rgb[((size_t)b * HW + p) * 3 + c] = u;
+        if (src_rgb) src_rgb[((size_t)b * HW + p) * 3 + c] = (float)((double)u / 127.5 - 1.0);   // :534
     }
     const float v = __fdiv_rn(__fadd_rn(d[(size_t)3 * HW + p], 1.0f), 2.0f);  // :906-911
     float o;
@@ -358,11 +360,11 @@ extern "C" int sgam_inverse_warp(const float *src_rgb, long long rgb_cs, long lo
 }
 
 extern "C" int sgam_frame_outputs(const float *dec, int B, int H, int W, int dataset, uint8_t *rgb_u8, float *depth,
-                                  void *stream) {
+                                  float *src_rgb, void *stream) {
     SGAM_REQUIRE(dec && rgb_u8 && depth && B > 0 && H > 0 && W > 0, "frame_outputs: bad arguments");
     SGAM_REQUIRE(dataset == SGAM_DATASET_CLEVR || dataset == SGAM_DATASET_GOOGLE_EARTH, "frame_outputs: bad dataset %d", dataset);
     dim3 grid(cdiv((long long)H * W, 256), B);
-    frame_outputs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dec, H * W, dataset, rgb_u8, depth);
+    frame_outputs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dec, H * W, dataset, rgb_u8, depth, src_rgb);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }

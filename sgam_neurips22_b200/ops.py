@@ -110,8 +110,9 @@ def inverse_warp(src_rgb, src_depth, tgt_depth, Kinv_tgt, proj, channels_last=Fa
     return (out, best) if want_best else out
 
 
-def frame_outputs(dec, dataset, rgb_u8=None, depth=None):
-    """inference_pipeline.py:893-911: dec [B,4,H,W] -> uint8 RGB [B,H,W,3], metric depth [B,H,W]."""
+def frame_outputs(dec, dataset, rgb_u8=None, depth=None, want_src_rgb=False):
+    """inference_pipeline.py:893-911: dec [B,4,H,W] -> uint8 RGB [B,H,W,3], metric depth [B,H,W]
+    (+ the fp32 source image u8/127.5-1 a later step would re-load, inference_pipeline.py:534)."""
     lib = _lib.load()
     _chk(dec, name="dec")
     B, C, H, W = dec.shape
@@ -121,9 +122,10 @@ def frame_outputs(dec, dataset, rgb_u8=None, depth=None):
         rgb_u8 = torch.empty(B, H, W, 3, dtype=torch.uint8, device=dec.device)
     if depth is None:
         depth = torch.empty(B, H, W, device=dec.device)
+    src = torch.empty(B, H, W, 3, device=dec.device) if want_src_rgb else None
     _lib.check(lib.sgam_frame_outputs(dec.data_ptr(), B, H, W, dataset_id(dataset), rgb_u8.data_ptr(),
-                                      depth.data_ptr(), _stream()), "sgam_frame_outputs")
-    return rgb_u8, depth
+                                      depth.data_ptr(), _ptr(src), _stream()), "sgam_frame_outputs")
+    return (rgb_u8, depth, src) if want_src_rgb else (rgb_u8, depth)
 
 
 # --------------------------------------------------------------------------------------------- stage (ii)
