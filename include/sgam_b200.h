@@ -139,6 +139,39 @@ int sgam_gemm_nt(const float *A, const float *Bm, float *C, const float *bias_m,
 /* Row softmax in place: x [rows, cols] (model.py:181). */
 int sgam_softmax_rows(float *x, long long rows, int cols, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stage (iii), tensor-core path (tcgen05 + TMA + TMEM).  Operands are split-bf16 planes: x = hi + lo with
+ * hi = bf16(x), lo = bf16(x - hi); products are accumulated as hi*hi + hi*lo + lo*hi in fp32 (nsplit = 3) or
+ * hi*hi only (nsplit = 1).  Same operators as above (model.py line references as for sgam_conv2d /
+ * sgam_groupnorm / sgam_gemm_nt / sgam_softmax_rows).
+ */
+
+/* fp32 NHWC [B,H,W,C] -> hi / lo bf16 [B,H<<up,W<<up,C] (nearest x2 up-sampling fused: Upsample, model.py:50). */
+int sgam_split_bf16(const float *x, void *hi, void *lo, int B, int H, int W, int C, int upsample, void *stream);
+
+/* GroupNorm(32, C, eps=1e-6) (+ swish) with split-bf16 output; partial as for sgam_groupnorm. */
+int sgam_groupnorm_split(const float *x, const float *gamma, const float *beta, void *hi, void *lo, double *partial,
+                         int B, long long HW, int C, int swish, void *stream);
+
+/* Row softmax of fp32 scores x [rows, cols] -> split-bf16 probabilities. */
+int sgam_softmax_split(const float *x, void *hi, void *lo, long long rows, int cols, void *stream);
+
+/* 1 if sgam_conv2d_tc has a kernel for this stride-1 conv shape. */
+int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int stride);
+
+/* Stride-1 conv 3x3 / 1x1 (symmetric padding) on tensor cores.  x_hi/x_lo [B,H,W,Cin] bf16, w_hi/w_lo
+ * [Cout, k*k*Cin] bf16 (K-major), bias [Cout] or NULL, residual [B,H,W,Cout] fp32 or NULL.
+ * Output fp32 y and/or split-bf16 y_hi/y_lo (either may be NULL). */
+int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
+                   const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
+                   int ksize, int nsplit, void *stream);
+
+/* Batched C = alpha * A . B^T (+ bias_m[row]) on tensor cores.  A [batch|1, M, K], B [batch|1, N, K] split-bf16
+ * (a_batched / b_batched say whether the operand has the batch dimension); output fp32 C and/or split-bf16. */
+int sgam_gemm_nt_tc(const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo, const float *bias_m,
+                    float *C, void *c_hi, void *c_lo, int batch, int M, int N, int K, int a_batched, int b_batched,
+                    float alpha, int nsplit, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

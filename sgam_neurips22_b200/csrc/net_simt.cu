@@ -395,6 +395,14 @@ softmax_rows_kernel(float *__restrict__ x, int cols) {
 
 }  // namespace
 
+// shared with net_tc.cu (GroupNorm statistics are the same kernel on both paths)
+int sgam_gn_stats_launch(const float *x, double *partial, int B, long long HW, int C, cudaStream_t s) {
+    const int S = sgam_gn_splits(HW);
+    gn_stats_kernel<<<dim3(S, B), 256, 0, s>>>(x, partial, HW, C, S);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
 extern "C" int sgam_stem_conv(const float *x, const uint8_t *mask, const float *w, const float *bias, int B, int H,
                               int W, float *y, void *stream) {
     SGAM_REQUIRE(x && w && bias && y && B > 0 && H > 0 && W > 0, "stem_conv: bad arguments");
@@ -459,8 +467,8 @@ extern "C" int sgam_groupnorm(const float *x, const float *gamma, const float *b
     SGAM_REQUIRE(B > 0 && HW > 0 && C % 128 == 0 && C <= 1024, "groupnorm: C=%d must be a multiple of 128 (<= 1024)", C);
     cudaStream_t s = (cudaStream_t)stream;
     const int S = sgam_gn_splits(HW);
-    gn_stats_kernel<<<dim3(S, B), 256, 0, s>>>(x, partial, HW, C, S);
-    SGAM_LAUNCH_OK();
+    int rc = sgam_gn_stats_launch(x, partial, B, HW, C, s);
+    if (rc) return rc;
     const long long total = HW * (C / 4);
     const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
     gn_apply_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, partial, gamma, beta, y, HW, C, S, swish);

@@ -1,0 +1,513 @@
+// Stage (iii), tensor-core path (sm_100a): conv 3x3 / 1x1 and the attention products as ONE implicit-GEMM
+// kernel on tcgen05.mma with TMA-staged operands and TMEM accumulators.
+//
+//   D[m, n] = alpha * sum_k A(m, k) * B[n, k]  (+ bias_n[n]) (+ bias_m[m]) (+ R[m, n])
+//
+// Precision: the north_star asks for 1e-3 rel fp32 on the decoded RGB-D, which single-pass bf16 (2e-2) and
+// single-pass tf32 (2-3e-3) both miss.  Operands are therefore kept as split bf16 pairs
+// x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) and every K-block issues three kind::f16 MMAs,
+// hi*hi + hi*lo + lo*hi, into the same fp32 TMEM accumulator (the dropped lo*lo term is <= 2^-16 relative).
+//
+// Operand staging: activations live in HBM as NHWC bf16 planes.  The A tile of an output-pixel block is one TMA
+// box {64 channels, BW, BH, 1} of the 4-D tensor map (C, W, H, B) shifted by the filter tap (kw-1, kh-1); the
+// out-of-bounds zero fill of TMA *is* the conv padding, so there is no im2col buffer and no bounds code.  The box
+// lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, exactly the K-major canonical layout the
+// UMMA shared-memory descriptor expects.  Weights are [N, taps*C] K-major bf16 planes read through a 3-D map.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue
+// (tcgen05.ld 32x32b, bias / residual / alpha, fp32 or split-bf16 stores).  3-stage mbarrier ring.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 in, fp32 accumulate), single CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B) | [46,48) version = 1 | [61,64) layout = SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t make_smem_desc(const void *tile) {
+    const uint64_t addr = (uint64_t)((smem_u32(tile) & 0x3FFFFu) >> 4);
+    return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// K-major A and B (0) @15/@16, N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ the GEMM kernel
+constexpr int BM = 128, BK = 64, STAGES = 3, TC_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KB
+
+struct TcParams {
+    // tiling of M: tile t -> (b, ty, tx); rows of the tile are (ly, lx) with lx < BW, ly < BH, BW*BH = 128
+    int tiles_x, tiles_y, BW, BH;
+    int Ho, Wo;                 // output pixel grid per batch element (plain GEMM: Ho = 1, Wo = M)
+    int taps, ks, pad;          // conv: ks*ks taps, symmetric pad; plain GEMM: taps = 1, ks = 1, pad = 0
+    int kblocks_per_tap;        // C / 64 (rounded up)
+    int N;                      // total output columns (row stride of D)
+    int nsplit;                 // 3 = hi*hi + hi*lo + lo*hi ; 1 = hi*hi only
+    int a_batched, b_batched;   // whether the operand has a batch dimension (else coordinate 0)
+    long long d_batch_stride;   // elements between batch slices of D / R
+    float alpha;
+    const float *bias_n, *bias_m, *R;
+    float *D;                   // fp32 output (or null)
+    __nv_bfloat16 *D_hi, *D_lo; // split-bf16 output (or null)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+               const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams p) {
+    constexpr int B_TILE_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024-B alignment
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
+    const int n0 = blockIdx.y * BN;
+    const int num_kb = p.taps * p.kblocks_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // one full warp allocates BN TMEM columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_TILE_BYTES + B_TILE_BYTES);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES, it = kb / STAGES;
+                mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+                uint8_t *st = smem + (size_t)s * STAGE_BYTES;
+                const int tap = kb / p.kblocks_per_tap, kc = kb - tap * p.kblocks_per_tap;
+                const int kh = tap / p.ks, kw = tap - kh * p.ks;
+                const int cx = tx * p.BW + kw - p.pad, cy = ty * p.BH + kh - p.pad;
+                const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
+                mbar_expect_tx(&full_bar[s], tx_bytes);
+                tma_load_4d(st, &mapA_hi, &full_bar[s], kc * BK, cx, cy, ab);
+                tma_load_3d(st + 2 * A_TILE_BYTES, &mapB_hi, &full_bar[s], kb * BK, n0, bb);
+                if (p.nsplit == 3) {
+                    tma_load_4d(st + A_TILE_BYTES, &mapA_lo, &full_bar[s], kc * BK, cx, cy, ab);
+                    tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapB_lo, &full_bar[s], kb * BK, n0, bb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES, it = kb / STAGES;
+                mbar_wait(&full_bar[s], it & 1);
+                tc_fence_after();
+                uint8_t *st = smem + (size_t)s * STAGE_BYTES;
+                const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_TILE_BYTES);
+                const uint64_t b_hi = make_smem_desc(st + 2 * A_TILE_BYTES), b_lo = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {            // UMMA_K = 16 bf16 = 32 B: advance the start address field by 2
+                    const uint64_t off = (uint64_t)(k * 2);
+                    umma_bf16(tmem_base, a_hi + off, b_hi + off, idesc, (kb | k) ? 1u : 0u);
+                    if (p.nsplit == 3) {
+                        umma_bf16(tmem_base, a_hi + off, b_lo + off, idesc, 1u);
+                        umma_bf16(tmem_base, a_lo + off, b_hi + off, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);                     // frees the stage when these MMAs retire
+            }
+            umma_commit(&tmem_full_bar);                        // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4).. =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                           // tile row = TMEM lane
+        const int ly = r / p.BW, lx = r - ly * p.BW;
+        const int oy = ty * p.BH + ly, ox = tx * p.BW + lx;
+        const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
+        const long long m = (long long)oy * p.Wo + ox;          // row within the batch slice
+        const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!row_ok) continue;
+            const int n = n0 + c0;
+            if (n >= p.N) continue;
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bm;
+            if (p.bias_n) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias_n + n + j));
+                    o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
+                }
+            }
+            if (p.R) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.R + row_off + n + j));
+                    o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+                }
+            }
+            if (p.D) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(p.D + row_off + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+            if (p.D_hi) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(o[j]), h1 = __float2bfloat16_rn(o[j + 1]);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(o[j] - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(o[j + 1] - __bfloat162float(h1));
+                    hi[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    *reinterpret_cast<uint4 *>(p.D_hi + row_off + n + 2 * j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+                    *reinterpret_cast<uint4 *>(p.D_lo + row_off + n + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {   // resolved through the runtime so that the library does not link libcuda (it must load on CPU-only hosts)
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+// bf16 tensor [d3][d2][d1][d0] (d0 innermost, contiguous), box {b0, b1, b2, 1}, 128-byte swizzle, zero OOB fill
+int make_map(CUtensorMap *m, const void *base, int rank, const long long *dims, const int *box) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { sgam_set_error("cuTensorMapEncodeTiled is unavailable"); return SGAM_ERR_CUDA; }
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bd[4], es[4];
+    unsigned long long stride = 2;
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = (cuuint64_t)dims[i]; bd[i] = (cuuint32_t)box[i]; es[i] = 1;
+        stride *= (unsigned long long)dims[i];
+        if (i < rank - 1) gs[i] = stride;
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bd, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { sgam_set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %lld %lld %lld)", (int)r, rank, dims[0], dims[1], rank > 2 ? dims[2] : 0); return SGAM_ERR_CUDA; }
+    return SGAM_OK;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, const TcParams &p,
+              int tiles_m, int N, cudaStream_t s) {
+    constexpr size_t smem = (size_t)STAGES * (2 * A_TILE_BYTES + 2 * BN * BK * 2) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(tiles_m, cdiv(N, BN));
+    tc_gemm_kernel<BN><<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ producers of split bf16
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+// x fp32 [B, H, W, C] -> hi / lo bf16 [B, H<<up, W<<up, C] (nearest x2 up-sampling fused when up = 1)
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+                  long long total_q, int H, int W, int CQ, int up) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_q; e += (long long)gridDim.x * blockDim.x) {
+        long long src = e;
+        if (up) {
+            const int cq = (int)(e % CQ);
+            long long pix = e / CQ;
+            const int Wo = W * 2, Ho = H * 2;
+            const int ox = (int)(pix % Wo); pix /= Wo;
+            const int oy = (int)(pix % Ho); const long long b = pix / Ho;
+            src = (((b * H + (oy >> 1)) * W + (ox >> 1)) * CQ) + cq;
+        }
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + src);
+        uint32_t h[2], l[2];
+        split2(v.x, v.y, h[0], l[0]);
+        split2(v.z, v.w, h[1], l[1]);
+        reinterpret_cast<uint2 *>(hi)[e] = make_uint2(h[0], h[1]);
+        reinterpret_cast<uint2 *>(lo)[e] = make_uint2(l[0], l[1]);
+    }
+}
+
+// GroupNorm apply (+ swish) with split-bf16 output; statistics come from gn_stats (net_simt.cu) partials
+__global__ void __launch_bounds__(256)
+gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ gamma,
+                      const float *__restrict__ beta, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+                      long long HW, int C, int S, int swish) {
+    __shared__ float mean_s[32], rstd_s[32];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (tid < 32) {
+        double a = 0.0, q = 0.0;
+        for (int s = 0; s < S; ++s) {
+            const double *src = partial + (((size_t)b * S + s) * 32 + tid) * 2;
+            a += src[0]; q += src[1];
+        }
+        const double n = (double)HW * (C / 32), mean = a / n;
+        double var = q / n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        mean_s[tid] = (float)mean;
+        rstd_s[tid] = (float)(1.0 / sqrt(var + 1e-6));
+    }
+    __syncthreads();
+    const int CQ = C / 4, cpg = C / 32;
+    const long long total = HW * CQ;
+    const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)b * HW * C);
+    uint2 *dh = reinterpret_cast<uint2 *>(hi + (size_t)b * HW * C), *dl = reinterpret_cast<uint2 *>(lo + (size_t)b * HW * C);
+    for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(e % CQ), c = cq * 4, g = c / cpg;
+        const float mu = mean_s[g], rs = rstd_s[g];
+        const float4 v = __ldg(src + e), ga = __ldg(reinterpret_cast<const float4 *>(gamma + c)),
+                     be = __ldg(reinterpret_cast<const float4 *>(beta + c));
+        float o[4] = {(v.x - mu) * rs * ga.x + be.x, (v.y - mu) * rs * ga.y + be.y,
+                      (v.z - mu) * rs * ga.z + be.z, (v.w - mu) * rs * ga.w + be.w};
+        if (swish) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.0f + expf(-o[k]));
+        }
+        uint32_t h[2], l[2];
+        split2(o[0], o[1], h[0], l[0]);
+        split2(o[2], o[3], h[1], l[1]);
+        dh[e] = make_uint2(h[0], h[1]);
+        dl[e] = make_uint2(l[0], l[1]);
+    }
+}
+
+// row softmax of fp32 scores -> split-bf16 probabilities (model.py:181); cols % 2 == 0
+__global__ void __launch_bounds__(256)
+softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cols) {
+    __shared__ float sh[32];
+    const float *row = x + (size_t)blockIdx.x * cols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, row[c]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sh[warp] = mx;
+    __syncthreads();
+    mx = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sh[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += expf(row[c] - mx);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) sh[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += sh[w];
+    const float inv = 1.0f / sum;
+    uint32_t *dh = reinterpret_cast<uint32_t *>(hi + (size_t)blockIdx.x * cols), *dl = reinterpret_cast<uint32_t *>(lo + (size_t)blockIdx.x * cols);
+    for (int c = threadIdx.x; c < cols / 2; c += blockDim.x) {
+        const float2 v = *reinterpret_cast<const float2 *>(row + 2 * c);
+        uint32_t h, l;
+        split2(expf(v.x - mx) * inv, expf(v.y - mx) * inv, h, l);
+        dh[c] = h; dl[c] = l;
+    }
+}
+
+}  // namespace
+
+// gn_stats launcher lives in net_simt.cu
+int sgam_gn_stats_launch(const float *x, double *partial, int B, long long HW, int C, cudaStream_t s);
+
+extern "C" int sgam_split_bf16(const float *x, void *hi, void *lo, int B, int H, int W, int C, int upsample, void *stream) {
+    SGAM_REQUIRE(x && hi && lo && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "split_bf16: bad arguments");
+    const long long total_q = (long long)B * (H << upsample) * (W << upsample) * (C / 4);
+    const unsigned blocks = (unsigned)min((long long)148 * 16, (total_q + 255) / 256);
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, total_q, H, W, C / 4, upsample);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const float *beta, void *hi, void *lo, double *partial,
+                                    int B, long long HW, int C, int swish, void *stream) {
+    SGAM_REQUIRE(x && gamma && beta && hi && lo && partial, "groupnorm_split: null pointer");
+    SGAM_REQUIRE(B > 0 && HW > 0 && C % 128 == 0 && C <= 1024, "groupnorm_split: C=%d must be a multiple of 128 (<= 1024)", C);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = sgam_gn_stats_launch(x, partial, B, HW, C, s);
+    if (rc) return rc;
+    const long long total = HW * (C / 4);
+    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
+    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, partial, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
+                                                          sgam_gn_splits(HW), swish);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long rows, int cols, void *stream) {
+    SGAM_REQUIRE(x && hi && lo && rows > 0 && cols > 0 && cols % 2 == 0, "softmax_split: bad arguments");
+    softmax_split_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, cols);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+static int pick_bw(int W) { return W >= 128 ? 128 : W; }
+
+extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int stride) {
+    const bool pow2 = (W & (W - 1)) == 0;
+    return (stride == 1) && (ksize == 1 || ksize == 3) && (Cin % 64 == 0) && (Cout % 32 == 0) && ((W % 128 == 0) || (pow2 && W <= 128)) && H > 0;
+}
+
+extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
+                              const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
+                              int ksize, int nsplit, void *stream) {
+    SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && (y || (y_hi && y_lo)), "conv2d_tc: null pointer");
+    SGAM_REQUIRE(sgam_tc_supported_conv(H, W, Cin, Cout, ksize, 1), "conv2d_tc: unsupported shape H=%d W=%d Cin=%d Cout=%d k=%d", H, W, Cin, Cout, ksize);
+    SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "conv2d_tc: nsplit must be 1 or 3");
+    const int BW = pick_bw(W), BH = 128 / BW;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    const long long adims[4] = {Cin, W, H, B};
+    const int abox[4] = {BK, BW, BH, 1};
+    const int taps = ksize * ksize;
+    const long long bdims[3] = {(long long)taps * Cin, Cout, 1};
+    const int BN = (Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32);
+    const int bbox[3] = {BK, BN, 1};
+    int rc;
+    if ((rc = make_map(&a_hi, x_hi, 4, adims, abox)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox)) ||
+        (rc = make_map(&b_hi, w_hi, 3, bdims, bbox)) || (rc = make_map(&b_lo, w_lo, 3, bdims, bbox)))
+        return rc;
+    TcParams p{};
+    p.tiles_x = cdiv(W, BW); p.tiles_y = cdiv(H, BH); p.BW = BW; p.BH = BH; p.Ho = H; p.Wo = W;
+    p.taps = taps; p.ks = ksize; p.pad = ksize / 2; p.kblocks_per_tap = Cin / BK; p.N = Cout; p.nsplit = nsplit;
+    p.a_batched = 1; p.b_batched = 0; p.d_batch_stride = (long long)H * W * Cout; p.alpha = 1.0f;
+    p.bias_n = bias; p.bias_m = nullptr; p.R = residual; p.D = y; p.D_hi = (__nv_bfloat16 *)y_hi; p.D_lo = (__nv_bfloat16 *)y_lo;
+    const int tiles_m = p.tiles_x * p.tiles_y * B;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (BN == 128) return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Cout, s);
+    if (BN == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Cout, s);
+    return launch_tc<32>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Cout, s);
+}
+
+extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const void *b_hi_p, const void *b_lo_p, const float *bias_m,
+                               float *C, void *c_hi, void *c_lo, int batch, int M, int N, int K, int a_batched, int b_batched,
+                               float alpha, int nsplit, void *stream) {
+    SGAM_REQUIRE(a_hi_p && a_lo_p && b_hi_p && b_lo_p && (C || (c_hi && c_lo)), "gemm_nt_tc: null pointer");
+    SGAM_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 32 == 0, "gemm_nt_tc: needs K %% 8 == 0 and N %% 32 == 0 (M=%d N=%d K=%d)", M, N, K);
+    SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_nt_tc: nsplit must be 1 or 3");
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    const long long adims[4] = {K, M, 1, a_batched ? batch : 1};
+    const int abox[4] = {BK, 128, 1, 1};
+    const long long bdims[3] = {K, N, b_batched ? batch : 1};
+    const int BN = (N % 128 == 0) ? 128 : ((N % 64 == 0) ? 64 : 32);
+    const int bbox[3] = {BK, BN, 1};
+    int rc;
+    if ((rc = make_map(&a_hi, a_hi_p, 4, adims, abox)) || (rc = make_map(&a_lo, a_lo_p, 4, adims, abox)) ||
+        (rc = make_map(&b_hi, b_hi_p, 3, bdims, bbox)) || (rc = make_map(&b_lo, b_lo_p, 3, bdims, bbox)))
+        return rc;
+    TcParams p{};
+    p.tiles_x = cdiv(M, 128); p.tiles_y = 1; p.BW = 128; p.BH = 1; p.Ho = 1; p.Wo = M;
+    p.taps = 1; p.ks = 1; p.pad = 0; p.kblocks_per_tap = cdiv(K, BK); p.N = N; p.nsplit = nsplit;
+    p.a_batched = a_batched; p.b_batched = b_batched; p.d_batch_stride = (long long)M * N; p.alpha = alpha;
+    p.bias_n = nullptr; p.bias_m = bias_m; p.R = nullptr; p.D = C; p.D_hi = (__nv_bfloat16 *)c_hi; p.D_lo = (__nv_bfloat16 *)c_lo;
+    const int tiles_m = p.tiles_x * batch;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (BN == 128) return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, N, s);
+    if (BN == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, N, s);
+    return launch_tc<32>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, N, s);
+}

@@ -8,6 +8,7 @@ the checkpoint, and every operator is a libsgam_b200 kernel.  There is no CPU pa
 `.to('cuda')` raises.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -74,6 +75,7 @@ class VQModel(torch.nn.Module):
         self.global_step = 0
         self.use_rgbd_integration = False
         self.splat_policy = ops.SPLAT_LAST_WRITER          # reference semantics; ops.SPLAT_ZMIN = z-buffered splat
+        self.engine_mode = os.environ.get("SGAM_ENGINE_MODE", "tc")   # "tc": tcgen05 split-bf16 convs; "simt": exact fp32
         if monitor is not None:
             self.monitor = monitor
         if remap is not None:
@@ -145,7 +147,7 @@ class VQModel(torch.nn.Module):
             if self.device.type != "cuda":
                 raise RuntimeError("VQModel: move the model to a CUDA device first (.to('cuda:0')); "
                                    "the B200 engine has no CPU fallback")
-            self._engine = VQGANEngine(self.state_dict(), self.ddconfig, self.device)
+            self._engine = VQGANEngine(self.state_dict(), self.ddconfig, self.device, mode=self.engine_mode)
         return self._engine
 
     def use_vq(self):

@@ -230,3 +230,104 @@ def softmax_rows_(x):
     cols = x.shape[-1]
     _lib.check(lib.sgam_softmax_rows(x.data_ptr(), x.numel() // cols, cols, _stream()), "sgam_softmax_rows")
     return x
+
+
+# ------------------------------------------------------------------------- stage (iii), tensor-core path
+def _bf16_pair(shape, device):
+    return (torch.empty(shape, dtype=torch.bfloat16, device=device), torch.empty(shape, dtype=torch.bfloat16, device=device))
+
+
+def split_bf16(x, upsample=0):
+    """fp32 NHWC [B,H,W,C] -> (hi, lo) bf16 [B,H<<up,W<<up,C] with x = hi + lo (+ fused nearest x2 up-sampling)."""
+    lib = _lib.load()
+    _chk(x, name="x")
+    B, H, W, C = x.shape
+    hi, lo = _bf16_pair((B, H << upsample, W << upsample, C), x.device)
+    _lib.check(lib.sgam_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, H, W, C, int(upsample), _stream()),
+               "sgam_split_bf16")
+    return hi, lo
+
+
+def split_weight(w):
+    """Host-side one-off split of a weight matrix [N, K] fp32 -> (hi, lo) bf16 (same rounding as the device split)."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def groupnorm_split(x, gamma, beta, swish, workspace=None):
+    """GroupNorm(32, C, eps=1e-6) (+ swish) -> (hi, lo) bf16 NHWC."""
+    lib = _lib.load()
+    _chk(x, name="x"), _chk(gamma, name="gamma"), _chk(beta, name="beta")
+    B, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C)
+    if workspace is None:
+        workspace = torch.empty(B * lib.sgam_gn_splits(HW) * 64, dtype=torch.float64, device=x.device)
+    hi, lo = _bf16_pair(tuple(x.shape), x.device)
+    _lib.check(lib.sgam_groupnorm_split(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+                                        workspace.data_ptr(), B, HW, C, int(swish), _stream()), "sgam_groupnorm_split")
+    return hi, lo
+
+
+def softmax_split(s):
+    """Row softmax of fp32 scores [..., cols] -> (hi, lo) bf16 probabilities."""
+    lib = _lib.load()
+    _chk(s, name="scores")
+    cols = s.shape[-1]
+    hi, lo = _bf16_pair(tuple(s.shape), s.device)
+    _lib.check(lib.sgam_softmax_split(s.data_ptr(), hi.data_ptr(), lo.data_ptr(), s.numel() // cols, cols, _stream()),
+               "sgam_softmax_split")
+    return hi, lo
+
+
+def tc_supported_conv(H, W, Cin, Cout, ksize, stride):
+    return bool(_lib.load().sgam_tc_supported_conv(H, W, Cin, Cout, ksize, stride))
+
+
+def conv2d_tc(x, w, bias, residual=None, ksize=3, out_f32=True, out_split=False, nsplit=3):
+    """Stride-1 conv on tcgen05.  x = (hi, lo) bf16 [B,H,W,Cin]; w = (hi, lo) bf16 [Cout, k*k*Cin]; bias fp32.
+    Returns fp32 y [B,H,W,Cout] and/or the (hi, lo) pair, as requested."""
+    lib = _lib.load()
+    x_hi, x_lo = x
+    w_hi, w_lo = w
+    for n, t in (("x_hi", x_hi), ("x_lo", x_lo), ("w_hi", w_hi), ("w_lo", w_lo)):
+        _chk(t, torch.bfloat16, n)
+    B, H, W, Cin = x_hi.shape
+    Cout = w_hi.shape[0]
+    if w_hi.shape[1] != ksize * ksize * Cin:
+        raise RuntimeError(f"conv2d_tc: weight {tuple(w_hi.shape)} does not match k={ksize} Cin={Cin}")
+    y = torch.empty(B, H, W, Cout, device=x_hi.device) if out_f32 else None
+    pair = _bf16_pair((B, H, W, Cout), x_hi.device) if out_split else (None, None)
+    if residual is not None:
+        _chk(residual, name="residual")
+    _lib.check(lib.sgam_conv2d_tc(x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), _ptr(bias),
+                                  _ptr(residual), _ptr(y), _ptr(pair[0]), _ptr(pair[1]), B, H, W, Cin, Cout, ksize,
+                                  nsplit, _stream()), "sgam_conv2d_tc")
+    if out_f32 and out_split:
+        return y, pair
+    return y if out_f32 else pair
+
+
+def gemm_nt_tc(a, b, bias_m=None, alpha=1.0, out_f32=True, out_split=False, nsplit=3):
+    """C = alpha * A . B^T (+ bias_m per row) on tcgen05.  a = (hi, lo) [batch, M, K] or [M, K] (shared);
+    b = (hi, lo) [batch, N, K] or [N, K] (shared).  Output [batch, M, N]."""
+    lib = _lib.load()
+    a_hi, a_lo = a
+    b_hi, b_lo = b
+    for n, t in (("a_hi", a_hi), ("a_lo", a_lo), ("b_hi", b_hi), ("b_lo", b_lo)):
+        _chk(t, torch.bfloat16, n)
+    a_b, b_b = a_hi.dim() == 3, b_hi.dim() == 3
+    batch = a_hi.shape[0] if a_b else (b_hi.shape[0] if b_b else 1)
+    M, K = a_hi.shape[-2:]
+    N = b_hi.shape[-2]
+    if b_hi.shape[-1] != K or (a_b and b_b and a_hi.shape[0] != b_hi.shape[0]):
+        raise RuntimeError(f"gemm_nt_tc: shapes {tuple(a_hi.shape)} x {tuple(b_hi.shape)}")
+    dev = a_hi.device
+    y = torch.empty(batch, M, N, device=dev) if out_f32 else None
+    pair = _bf16_pair((batch, M, N), dev) if out_split else (None, None)
+    _lib.check(lib.sgam_gemm_nt_tc(a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), _ptr(bias_m),
+                                   _ptr(y), _ptr(pair[0]), _ptr(pair[1]), batch, M, N, K, int(a_b), int(b_b), float(alpha),
+                                   nsplit, _stream()), "sgam_gemm_nt_tc")
+    if out_f32 and out_split:
+        return y, pair
+    return y if out_f32 else pair

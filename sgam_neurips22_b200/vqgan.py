@@ -20,12 +20,20 @@ def _pack_conv(w):
 
 
 class VQGANEngine:
-    def __init__(self, state_dict, ddconfig, device="cuda:0"):
+    """mode "tc"  : convolutions and attention products on tcgen05 tensor cores with split-bf16 operands
+                     (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM); odd-shaped layers stay on the fp32 kernels.
+       mode "simt": every layer on the exact-fp32 CUDA-core kernels (the on-device reference of the tc path)."""
+
+    def __init__(self, state_dict, ddconfig, device="cuda:0", mode="tc", nsplit=3):
         self.dd = dict(ddconfig)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("VQGANEngine runs on a CUDA device only (no CPU fallback)")
+        if mode not in ("tc", "simt"):
+            raise ValueError(mode)
+        self.mode, self.nsplit = mode, nsplit
         self.p = {}
+        self.wsplit = {}
         self.load_state_dict(state_dict)
 
     # ------------------------------------------------------------------ weights
@@ -46,34 +54,79 @@ class VQGANEngine:
             raise KeyError(f"state_dict lacks hot-path tensors: {missing}")
         self.p = p
         self.n_embed, self.embed_dim = p["quantize.embedding.weight"].shape
+        self.wsplit = {}
+        if self.mode == "tc":
+            for k, v in p.items():
+                if k.endswith(".weight") and v.dim() == 2 and k != "quantize.embedding.weight" and v.shape[1] % 64 == 0 \
+                        and v.shape[0] % 32 == 0:
+                    self.wsplit[k[:-len(".weight")]] = ops.split_weight(v)
 
     def has(self, name):
         return f"{name}.weight" in self.p
 
     # ------------------------------------------------------------------ blocks (NHWC)
     def conv(self, name, x, **kw):
+        """fp32 CUDA-core conv (sgam_conv2d)."""
         return ops.conv2d(x, self.p[f"{name}.weight"], self.p[f"{name}.bias"], **kw)
 
     def norm(self, name, x, swish):
         return ops.groupnorm(x, self.p[f"{name}.weight"], self.p[f"{name}.bias"], swish)
 
+    def norm_split(self, name, x, swish):
+        return ops.groupnorm_split(x, self.p[f"{name}.weight"], self.p[f"{name}.bias"], swish)
+
+    def tc_ok(self, name, x_shape, ksize, stride=1):
+        if self.mode != "tc" or name not in self.wsplit:
+            return False
+        B, H, W, Cin = x_shape
+        return ops.tc_supported_conv(H, W, Cin, self.p[f"{name}.weight"].shape[0], ksize, stride)
+
+    def conv_tc(self, name, xs, ksize, **kw):
+        """tcgen05 conv on a split-bf16 activation pair."""
+        return ops.conv2d_tc(xs, self.wsplit[name], self.p[f"{name}.bias"], ksize=ksize, nsplit=self.nsplit, **kw)
+
+    def conv_from_f32(self, name, x, ksize, upsample=0, residual=None):
+        """conv of an fp32 activation: split (+ fused x2 up-sampling) then tcgen05, or the fp32 kernel."""
+        B, H, W, C = x.shape
+        if self.tc_ok(name, (B, H << upsample, W << upsample, C), ksize):
+            return self.conv_tc(name, ops.split_bf16(x, upsample), ksize, residual=residual)
+        return self.conv(name, x, ksize=ksize, upsample=upsample, residual=residual)
+
+    def norm_conv(self, norm_name, conv_name, x, residual=None):
+        """GroupNorm + swish + 3x3 conv (the ResnetBlock / norm_out pattern)."""
+        if self.tc_ok(conv_name, x.shape, 3):
+            return self.conv_tc(conv_name, self.norm_split(norm_name, x, True), 3, residual=residual)
+        return self.conv(conv_name, self.norm(norm_name, x, True), ksize=3, residual=residual)
+
     def resnet_block(self, name, x):
         """model.py:78-137 with temb=None, dropout 0."""
-        h = self.conv(f"{name}.conv1", self.norm(f"{name}.norm1", x, True), ksize=3)
-        h = self.norm(f"{name}.norm2", h, True)
+        h = self.norm_conv(f"{name}.norm1", f"{name}.conv1", x)
         if self.has(f"{name}.nin_shortcut"):
-            x = self.conv(f"{name}.nin_shortcut", x, ksize=1)
-        return self.conv(f"{name}.conv2", h, ksize=3, residual=x)
+            x = self.conv_from_f32(f"{name}.nin_shortcut", x, 1)
+        return self.norm_conv(f"{name}.norm2", f"{name}.conv2", h, residual=x)
 
     def attn_block(self, name, x):
         """model.py:140-192: single-head spatial self-attention over H*W tokens."""
         B, H, W, C = x.shape
+        T = H * W
+        scale = float(int(C) ** (-0.5))
+        if self.mode == "tc" and f"{name}.q" in self.wsplit and T % 8 == 0 and T % 32 == 0 and self.tc_ok(f"{name}.q", x.shape, 1):
+            hs = self.norm_split(f"{name}.norm", x, False)
+            q = self.conv_tc(f"{name}.q", hs, 1, out_f32=False, out_split=True)
+            k = self.conv_tc(f"{name}.k", hs, 1, out_f32=False, out_split=True)
+            flat = lambda pair, shape: (pair[0].view(shape), pair[1].view(shape))
+            # V^T [B, C, T] = W_v . h^T + b_v (bias per row), so that P.V is another A.B^T product
+            vT = ops.gemm_nt_tc(self.wsplit[f"{name}.v"], flat(hs, (B, T, C)), bias_m=self.p[f"{name}.v.bias"],
+                                out_f32=False, out_split=True, nsplit=self.nsplit)
+            s = ops.gemm_nt_tc(flat(q, (B, T, C)), flat(k, (B, T, C)), alpha=scale, nsplit=self.nsplit)    # [B, T, T] fp32
+            p = ops.softmax_split(s)
+            o = ops.gemm_nt_tc(p, vT, out_f32=False, out_split=True, nsplit=self.nsplit)                    # [B, T, C]
+            return self.conv_tc(f"{name}.proj_out", flat(o, (B, H, W, C)), 1, residual=x)
         h_ = self.norm(f"{name}.norm", x, False)
-        q = self.conv(f"{name}.q", h_, ksize=1).view(B, H * W, C)
-        k = self.conv(f"{name}.k", h_, ksize=1).view(B, H * W, C)
-        # V^T [B, C, tokens] = W_v . h^T + b_v (per row), so that P.V is another A.B^T product
-        vT = ops.gemm_nt(self.p[f"{name}.v.weight"], h_.view(B, H * W, C), bias_m=self.p[f"{name}.v.bias"])
-        s = ops.gemm_nt(q, k, alpha=float(int(C) ** (-0.5)))          # [B, tokens, tokens]
+        q = self.conv(f"{name}.q", h_, ksize=1).view(B, T, C)
+        k = self.conv(f"{name}.k", h_, ksize=1).view(B, T, C)
+        vT = ops.gemm_nt(self.p[f"{name}.v.weight"], h_.view(B, T, C), bias_m=self.p[f"{name}.v.bias"])
+        s = ops.gemm_nt(q, k, alpha=scale)
         ops.softmax_rows_(s)
         o = ops.gemm_nt(s, vT).view(B, H, W, C)
         return self.conv(f"{name}.proj_out", o, ksize=1, residual=x)
@@ -82,7 +135,7 @@ class VQGANEngine:
     def encoder(self, h):
         dd = self.dd
         nres, nrb = len(dd["ch_mult"]), dd["num_res_blocks"]
-        h = self.conv("encoder.conv_in", h, ksize=3)
+        h = self.conv("encoder.conv_in", h, ksize=3)                      # Cin = 4: fp32 kernel
         for l in range(nres):
             for b in range(nrb):
                 h = self.resnet_block(f"encoder.down.{l}.block.{b}", h)
@@ -93,12 +146,12 @@ class VQGANEngine:
         h = self.resnet_block("encoder.mid.block_1", h)
         h = self.attn_block("encoder.mid.attn_1", h)
         h = self.resnet_block("encoder.mid.block_2", h)
-        return self.conv("encoder.conv_out", self.norm("encoder.norm_out", h, True), ksize=3)
+        return self.norm_conv("encoder.norm_out", "encoder.conv_out", h)
 
     def decoder(self, z):
         dd = self.dd
         nres, nrb = len(dd["ch_mult"]), dd["num_res_blocks"]
-        h = self.conv("decoder.conv_in", z, ksize=3)
+        h = self.conv_from_f32("decoder.conv_in", z, 3)
         h = self.resnet_block("decoder.mid.block_1", h)
         h = self.attn_block("decoder.mid.attn_1", h)
         h = self.resnet_block("decoder.mid.block_2", h)
@@ -108,9 +161,9 @@ class VQGANEngine:
                 if self.has(f"decoder.up.{l}.attn.{b}.norm"):
                     h = self.attn_block(f"decoder.up.{l}.attn.{b}", h)
             if l != 0:
-                h = self.conv(f"decoder.up.{l}.upsample.conv", h, ksize=3, upsample=1)
+                h = self.conv_from_f32(f"decoder.up.{l}.upsample.conv", h, 3, upsample=1)
         h = self.norm("decoder.norm_out", h, True)
-        return self.conv("decoder.conv_out", h, ksize=3, out_nchw=True)        # [B, out_ch, H, W]
+        return self.conv("decoder.conv_out", h, ksize=3, out_nchw=True)        # [B, out_ch, H, W]; Cout = 4: fp32 head kernel
 
     # ------------------------------------------------------------------ VQModel pieces
     def encode(self, x, mask=None):
@@ -119,7 +172,7 @@ class VQGANEngine:
             mask = mask.reshape(mask.shape[0], *mask.shape[-2:])
         h = ops.stem_conv(x, mask, self.p["conv_in.weight"], self.p["conv_in.bias"])
         h = self.encoder(h)
-        return self.conv("quant_conv", h, ksize=1)
+        return self.conv_from_f32("quant_conv", h, 1)
 
     def quantize(self, pre_quant):
         """quantize.py:275-319 / :344-381 (topk=1): NHWC latent -> idx [B,h,w] int64, z_q NHWC."""
@@ -129,7 +182,7 @@ class VQGANEngine:
 
     def decode(self, z_q):
         """model.py:131-134: NHWC quantised latent -> dec [B,4,H,W] NCHW."""
-        return self.decoder(self.conv("post_quant_conv", z_q, ksize=1))
+        return self.decoder(self.conv_from_f32("post_quant_conv", z_q, 1))
 
     def embed_code(self, idx):
         """Codebook gather for decode_code (model.py:136-139): idx [B,h,w] -> NHWC latent."""

@@ -278,7 +278,7 @@ def engines(state_dicts):
 
     def get(ds):
         if ds not in cache:
-            cache[ds] = VQGANEngine(state_dicts(ds), recipes.DDCONFIG, "cuda:0")
+            cache[ds] = VQGANEngine(state_dicts(ds), recipes.DDCONFIG, "cuda:0", mode="simt")
         return cache[ds]
     return get
 

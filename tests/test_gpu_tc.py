@@ -1,0 +1,141 @@
+"""GPU tests of the tensor-core (tcgen05 / TMA / TMEM) path, through the C ABI.  Tolerances: the split-bf16 product
+hi*hi + hi*lo + lo*hi is accurate to ~2^-16 per term; unit ops are held to 5e-5 rel-L2 against fp64, the whole network
+to the north_star's 1e-3 against the reference's CPU output, and the tokens must equal the reference's."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import recipes
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from sgam_neurips22_b200 import ops as _ops
+    return _ops
+
+
+def test_split_producers(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 6, 10, 128, generator=g) * 3
+    hi, lo = ops.split_bf16(x.cuda())
+    assert hi.dtype == torch.bfloat16 and torch.equal(hi.cpu(), x.to(torch.bfloat16))
+    assert rel(hi.float() + lo.float(), x) < 2e-5
+    hi, lo = ops.split_bf16(x.cuda(), upsample=1)
+    up = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert tuple(hi.shape) == (2, 12, 20, 128) and rel(hi.float() + lo.float(), up) < 2e-5
+    for C, hw in [(128, (12, 16)), (512, (4, 4))]:
+        x = torch.randn(2, C, *hw, generator=g) * 2 + 3
+        ga, be = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        for swish in (False, True):
+            ref = F.group_norm(x, 32, ga, be, eps=1e-6)
+            ref = ref * torch.sigmoid(ref) if swish else ref
+            hi, lo = ops.groupnorm_split(x.permute(0, 2, 3, 1).contiguous().cuda(), ga.cuda(), be.cuda(), swish)
+            assert rel((hi.float() + lo.float()).permute(0, 3, 1, 2), ref) < 2e-5
+    s = torch.randn(3, 50, 256, generator=g) * 4
+    hi, lo = ops.softmax_split(s.cuda())
+    assert rel(hi.float() + lo.float(), torch.softmax(s.double(), -1)) < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 128, 64), (2, 384, 256, 192), (1, 16, 32, 16), (2, 200, 96, 72), (1, 4096, 4096, 256)])
+def test_gemm_nt_tc(ops, shape):
+    batch, M, N, K = shape
+    g = torch.Generator().manual_seed(M + N)
+    A, B = torch.randn(batch, M, K, generator=g), torch.randn(batch, N, K, generator=g)
+    bm = torch.randn(M, generator=g)
+    a, b = ops.split_weight(A.cuda()), ops.split_weight(B.cuda())
+    ref = 0.25 * (A.double() @ B.double().transpose(1, 2)) + bm.double()[None, :, None]
+    y, (yh, yl) = ops.gemm_nt_tc(a, b, bias_m=bm.cuda(), alpha=0.25, out_split=True)
+    assert rel(y, ref) < 5e-5
+    assert rel(yh.float() + yl.float(), ref) < 5e-5
+    # shared (un-batched) A operand, as in V^T = W_v . h^T
+    a2 = ops.split_weight(A[0].contiguous().cuda())
+    y2 = ops.gemm_nt_tc(a2, b, alpha=1.0)
+    assert rel(y2, A[0].double()[None] @ B.double().transpose(1, 2)) < 5e-5
+    # single-term product is plain bf16
+    y1 = ops.gemm_nt_tc(a, b, nsplit=1)
+    assert 1e-4 < rel(y1, A.double() @ B.double().transpose(1, 2)) < 2e-2
+
+
+CONV_TC = [(1, 16, 16, 128, 128, 3), (2, 32, 32, 128, 256, 3), (1, 64, 64, 256, 256, 1), (1, 4, 4, 512, 512, 3),
+           (1, 256, 256, 128, 128, 3), (1, 8, 8, 256, 32, 1), (3, 128, 128, 128, 128, 3), (1, 2, 2, 512, 256, 3)]
+
+
+@pytest.mark.parametrize("case", CONV_TC)
+def test_conv2d_tc(ops, case):
+    B, H, W, Cin, Cout, ks = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, ks, ks, generator=g) / (Cin * ks * ks) ** 0.5
+    bias, r = torch.randn(Cout, generator=g), torch.randn(B, Cout, H, W, generator=g)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=ks // 2) + r.double()
+    assert ops.tc_supported_conv(H, W, Cin, Cout, ks, 1)
+    xs = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda())
+    ws = ops.split_weight(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda())
+    y, (yh, yl) = ops.conv2d_tc(xs, ws, bias.cuda(), residual=r.permute(0, 2, 3, 1).contiguous().cuda(), ksize=ks, out_split=True)
+    assert rel(y.permute(0, 3, 1, 2), ref) < 5e-5
+    assert rel((yh.float() + yl.float()).permute(0, 3, 1, 2), ref) < 5e-5
+    assert not ops.tc_supported_conv(H, W, 4, Cout, ks, 1) and not ops.tc_supported_conv(H, W, Cin, Cout, ks, 2)
+
+
+@pytest.fixture(scope="module")
+def engines(state_dicts):
+    from sgam_neurips22_b200.vqgan import VQGANEngine
+    cache = {}
+
+    def get(ds, mode):
+        if (ds, mode) not in cache:
+            cache[(ds, mode)] = VQGANEngine(state_dicts(ds), recipes.DDCONFIG, "cuda:0", mode=mode)
+        return cache[(ds, mode)]
+    return get
+
+
+@pytest.mark.parametrize("ds", ["clevr-infinite", "google_earth"])
+def test_tc_network_vs_reference_and_simt(golden, engines, ds):
+    tc, simt = engines(ds, "tc"), engines(ds, "simt")
+    rng = np.random.default_rng(51)
+    xin = torch.from_numpy(rng.uniform(-1, 1, (1, 4, 64, 64)).astype(np.float32)).cuda()
+    mk = torch.from_numpy((rng.random((1, 1, 64, 64)) < 0.3)).to(torch.uint8).cuda()
+    dec, pre, zq, idx = tc.forward(xin, mk)
+    dec_s, pre_s, _, idx_s = simt.forward(xin, mk)
+    assert rel(pre, pre_s) < 2e-4 and rel(dec, dec_s) < 2e-4 and torch.equal(idx, idx_s)
+    assert rel(pre.permute(0, 3, 1, 2), golden[f"net64.{ds}.pre_quant"]) < 1e-3
+    assert np.array_equal(idx.cpu().numpy()[0], golden[f"net64.{ds}.idx"])
+    assert rel(dec, golden[f"net64.{ds}.dec"]) < 1e-3
+
+
+def test_tc_config1_128(golden, engines):
+    torch.manual_seed(0)
+    x = torch.randn(1, 4, 128, 128)
+    dec, pre, zq, idx = engines("clevr-infinite", "tc").forward(x.cuda(), None)
+    assert rel(dec, golden["cfg1.dec"]) < 1e-3
+
+
+@pytest.mark.parametrize("ds", ["clevr-infinite", "google_earth"])
+def test_tc_full_step_256(golden, engines, ds):
+    """configs[1] / configs[2]-shaped step at 256x256 on the tensor-core path: the reference's tokens, decoded RGB-D
+    within 1e-3 rel (north_star), through the drop-in VQModel API."""
+    from oracle import model as omodel
+    from sgam_neurips22_b200 import ops as _ops
+    eng = engines(ds, "tc")
+    batch = recipes.scene_step_inputs(ds, 61, res=256, batch=1)
+    Ks = batch["Ks"]
+    Kinv = torch.from_numpy(Ks.reshape(-1, 3, 3)).inverse().reshape(Ks.shape).contiguous()
+    T = torch.from_numpy(omodel.src2tgt_transforms(batch["R_rels"], batch["t_rels"]))
+    d = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    g = _ops.splat_forward(d(batch["src_imgs"]), d(batch["src_depths"]), d(Ks[:, 0]), Kinv.cuda().contiguous(), T.cuda().contiguous(), ds, channels_last=True)
+    dec, pre, zq, idx = eng.forward(g["x"], g["mask"])
+    gap = golden[f"step256.{ds}.gap"]
+    same = idx.cpu().numpy()[0] == golden[f"step256.{ds}.idx"]
+    assert same.all(), f"token mismatches at oracle top-2 gaps {gap[~same.reshape(-1)]}"
+    assert rel(pre.permute(0, 3, 1, 2), golden[f"step256.{ds}.pre_quant"]) < 1e-3
+    assert rel(dec[:, :, ::4, ::4], golden[f"step256.{ds}.dec_sub"]) < 1e-3
+    print(ds, "pre rel", rel(pre.permute(0, 3, 1, 2), golden[f"step256.{ds}.pre_quant"]), "dec rel", rel(dec[:, :, ::4, ::4], golden[f"step256.{ds}.dec_sub"]))
