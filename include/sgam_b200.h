@@ -156,15 +156,16 @@ int sgam_groupnorm_split(const float *x, const float *gamma, const float *beta, 
 /* Row softmax of fp32 scores x [rows, cols] -> split-bf16 probabilities. */
 int sgam_softmax_split(const float *x, void *hi, void *lo, long long rows, int cols, void *stream);
 
-/* 1 if sgam_conv2d_tc has a kernel for this stride-1 conv shape. */
+/* 1 if sgam_conv2d_tc has a kernel for a conv whose OUTPUT grid is H x W. */
 int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int stride);
 
-/* Stride-1 conv 3x3 / 1x1 (symmetric padding) on tensor cores.  x_hi/x_lo [B,H,W,Cin] bf16, w_hi/w_lo
- * [Cout, k*k*Cin] bf16 (K-major), bias [Cout] or NULL, residual [B,H,W,Cout] fp32 or NULL.
- * Output fp32 y and/or split-bf16 y_hi/y_lo (either may be NULL). */
+/* Conv 3x3 / 1x1 on tensor cores: stride 1 with symmetric padding, or stride 2 = the Downsample (zero pad right /
+ * bottom, 3x3, model.py:68-72; strided TMA box).  x_hi/x_lo [B,H,W,Cin] bf16; w_hi/w_lo [ceil32(Cout), k*k*Cin]
+ * bf16 K-major (rows beyond Cout zero); bias [Cout] or NULL; residual [B,Ho,Wo,Cout] fp32 or NULL.
+ * Output fp32 y (NHWC, or [B,Cout,Ho,Wo] when out_nchw: the decoder head) and/or split-bf16 y_hi/y_lo. */
 int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                    const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
-                   int ksize, int nsplit, void *stream);
+                   int ksize, int stride, int out_nchw, int nsplit, void *stream);
 
 /* Batched C = alpha * A . B^T (+ bias_m[row]) on tensor cores.  A [batch|1, M, K], B [batch|1, N, K] split-bf16
  * (a_batched / b_batched say whether the operand has the batch dimension); output fp32 C and/or split-bf16. */

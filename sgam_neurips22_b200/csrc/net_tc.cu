@@ -99,9 +99,11 @@ struct TcParams {
     // tiling of M: tile t -> (b, ty, tx); rows of the tile are (ly, lx) with lx < BW, ly < BH, BW*BH = 128
     int tiles_x, tiles_y, BW, BH;
     int Ho, Wo;                 // output pixel grid per batch element (plain GEMM: Ho = 1, Wo = M)
-    int taps, ks, pad;          // conv: ks*ks taps, symmetric pad; plain GEMM: taps = 1, ks = 1, pad = 0
+    int taps, ks, pad, stride;  // conv: ks*ks taps, left/top pad, stride; plain GEMM: taps = 1, ks = 1, pad = 0, stride = 1
     int kblocks_per_tap;        // C / 64 (rounded up)
     int N;                      // total output columns (row stride of D)
+    int n_valid;                // columns actually stored (< N only for the zero-padded small-Cout head)
+    int out_nchw;               // store D as [b][n][oy][ox] (decoder conv_out) instead of row-major [m][n]
     int nsplit;                 // 3 = hi*hi + hi*lo + lo*hi ; 1 = hi*hi only
     int a_batched, b_batched;   // whether the operand has a batch dimension (else coordinate 0)
     long long d_batch_stride;   // elements between batch slices of D / R
@@ -154,7 +156,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 uint8_t *st = smem + (size_t)s * STAGE_BYTES;
                 const int tap = kb / p.kblocks_per_tap, kc = kb - tap * p.kblocks_per_tap;
                 const int kh = tap / p.ks, kw = tap - kh * p.ks;
-                const int cx = tx * p.BW + kw - p.pad, cy = ty * p.BH + kh - p.pad;
+                const int cx = tx * p.BW * p.stride + kw - p.pad, cy = ty * p.BH * p.stride + kh - p.pad;
                 const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
                 mbar_expect_tx(&full_bar[s], tx_bytes);
                 tma_load_4d(st, &mapA_hi, &full_bar[s], kc * BK, cx, cy, ab);
@@ -207,10 +209,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (!row_ok) continue;
             const int n = n0 + c0;
-            if (n >= p.N) continue;
+            if (n >= p.n_valid) continue;
             float o[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bm;
+            if (p.out_nchw || n + 32 > p.n_valid) {      // ragged / NCHW tail (the 4-channel head): scalar stores, coalesced over ox
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (n + j < p.n_valid) {
+                        float val = o[j] + (p.bias_n ? __ldg(p.bias_n + n + j) : 0.0f);
+                        if (p.out_nchw) p.D[(((long long)b * p.n_valid + n + j) * p.Ho + oy) * p.Wo + ox] = val;
+                        else p.D[row_off + n + j] = val + (p.R ? __ldg(p.R + row_off + n + j) : 0.0f);
+                    }
+                }
+                continue;
+            }
             if (p.bias_n) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -273,14 +286,14 @@ EncodeTiledFn get_encode() {
 }
 
 // bf16 tensor [d3][d2][d1][d0] (d0 innermost, contiguous), box {b0, b1, b2, 1}, 128-byte swizzle, zero OOB fill
-int make_map(CUtensorMap *m, const void *base, int rank, const long long *dims, const int *box) {
+int make_map(CUtensorMap *m, const void *base, int rank, const long long *dims, const int *box, const int *estride = nullptr) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { sgam_set_error("cuTensorMapEncodeTiled is unavailable"); return SGAM_ERR_CUDA; }
     cuuint64_t gd[4], gs[3];
     cuuint32_t bd[4], es[4];
     unsigned long long stride = 2;
     for (int i = 0; i < rank; ++i) {
-        gd[i] = (cuuint64_t)dims[i]; bd[i] = (cuuint32_t)box[i]; es[i] = 1;
+        gd[i] = (cuuint64_t)dims[i]; bd[i] = (cuuint32_t)box[i]; es[i] = estride ? (cuuint32_t)estride[i] : 1;
         stride *= (unsigned long long)dims[i];
         if (i < rank - 1) gs[i] = stride;
     }
@@ -380,34 +393,61 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
     }
 }
 
-// row softmax of fp32 scores -> split-bf16 probabilities (model.py:181); cols % 2 == 0
+// row softmax of fp32 scores -> split-bf16 probabilities (model.py:181); cols % 2 == 0.
+// VPT > 0: the row (cols <= 256*2*VPT) is read ONCE into registers (8 B in, 8 B out per pair); VPT = 0: three-pass fallback.
+template <int VPT>
 __global__ void __launch_bounds__(256)
 softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cols) {
-    __shared__ float sh[32];
+    __shared__ float sh[8];
     const float *row = x + (size_t)blockIdx.x * cols;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = cols / 2;
+    uint32_t *dh = reinterpret_cast<uint32_t *>(hi + (size_t)blockIdx.x * cols), *dl = reinterpret_cast<uint32_t *>(lo + (size_t)blockIdx.x * cols);
+    float2 v[VPT > 0 ? VPT : 1];
     float mx = -INFINITY;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, row[c]);
+    if (VPT > 0) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int c = threadIdx.x + i * 256;
+            v[i] = (c < half) ? __ldg(reinterpret_cast<const float2 *>(row) + c) : make_float2(-INFINITY, -INFINITY);
+            mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
+        }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, row[c]);
+    }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) sh[warp] = mx;
     __syncthreads();
     mx = sh[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sh[w]);
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
     __syncthreads();
     float sum = 0.f;
-    for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += expf(row[c] - mx);
+    if (VPT > 0) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) { v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx); sum += v[i].x + v[i].y; }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += 256) sum += expf(row[c] - mx);
+    }
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) sh[warp] = sum;
     __syncthreads();
     sum = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += sh[w];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += sh[w];
     const float inv = 1.0f / sum;
-    uint32_t *dh = reinterpret_cast<uint32_t *>(hi + (size_t)blockIdx.x * cols), *dl = reinterpret_cast<uint32_t *>(lo + (size_t)blockIdx.x * cols);
-    for (int c = threadIdx.x; c < cols / 2; c += blockDim.x) {
-        const float2 v = *reinterpret_cast<const float2 *>(row + 2 * c);
-        uint32_t h, l;
-        split2(expf(v.x - mx) * inv, expf(v.y - mx) * inv, h, l);
-        dh[c] = h; dl[c] = l;
+    if (VPT > 0) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int c = threadIdx.x + i * 256;
+            if (c < half) { uint32_t h, l; split2(v[i].x * inv, v[i].y * inv, h, l); dh[c] = h; dl[c] = l; }
+        }
+    } else {
+        for (int c = threadIdx.x; c < half; c += 256) {
+            const float2 t = *reinterpret_cast<const float2 *>(row + 2 * c);
+            uint32_t h, l;
+            split2(expf(t.x - mx) * inv, expf(t.y - mx) * inv, h, l);
+            dh[c] = h; dl[c] = l;
+        }
     }
 }
 
@@ -442,7 +482,13 @@ extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const fl
 
 extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long rows, int cols, void *stream) {
     SGAM_REQUIRE(x && hi && lo && rows > 0 && cols > 0 && cols % 2 == 0, "softmax_split: bad arguments");
-    softmax_split_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, cols);
+    cudaStream_t s = (cudaStream_t)stream;
+    __nv_bfloat16 *h = (__nv_bfloat16 *)hi, *l = (__nv_bfloat16 *)lo;
+    if (cols <= 512) softmax_split_kernel<1><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else if (cols <= 2048) softmax_split_kernel<4><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else if (cols <= 4096) softmax_split_kernel<8><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else if (cols <= 16384) softmax_split_kernel<32><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else softmax_split_kernel<0><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
@@ -450,38 +496,48 @@ extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long 
 static int pick_bw(int W) { return W >= 128 ? 128 : W; }
 
 extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int stride) {
+    // H, W: OUTPUT grid.  stride 2 is the Downsample (pad right/bottom, model.py:68-72).
     const bool pow2 = (W & (W - 1)) == 0;
-    return (stride == 1) && (ksize == 1 || ksize == 3) && (Cin % 64 == 0) && (Cout % 32 == 0) && ((W % 128 == 0) || (pow2 && W <= 128)) && H > 0;
+    return (stride == 1 || (stride == 2 && ksize == 3)) && (ksize == 1 || ksize == 3) && (Cin % 64 == 0) &&
+           (Cout % 32 == 0 || Cout <= 32) && ((W % 128 == 0) || (pow2 && W <= 128)) && H > 0;
 }
 
 extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                               const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
-                              int ksize, int nsplit, void *stream) {
+                              int ksize, int stride, int out_nchw, int nsplit, void *stream) {
     SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && (y || (y_hi && y_lo)), "conv2d_tc: null pointer");
-    SGAM_REQUIRE(sgam_tc_supported_conv(H, W, Cin, Cout, ksize, 1), "conv2d_tc: unsupported shape H=%d W=%d Cin=%d Cout=%d k=%d", H, W, Cin, Cout, ksize);
+    SGAM_REQUIRE(stride == 1 || stride == 2, "conv2d_tc: stride %d", stride);
+    const int Ho = H / stride, Wo = W / stride;        // stride 1: same; stride 2: pad (0,1,0,1) then 3x3/2 -> H/2 (even H)
+    SGAM_REQUIRE(H % stride == 0 && W % stride == 0, "conv2d_tc: odd extent with stride 2");
+    SGAM_REQUIRE(sgam_tc_supported_conv(Ho, Wo, Cin, Cout, ksize, stride), "conv2d_tc: unsupported shape H=%d W=%d Cin=%d Cout=%d k=%d s=%d", H, W, Cin, Cout, ksize, stride);
     SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "conv2d_tc: nsplit must be 1 or 3");
-    const int BW = pick_bw(W), BH = 128 / BW;
+    const int Npad = (Cout + 31) / 32 * 32;             // weight planes carry Npad rows (zero rows beyond Cout)
+    SGAM_REQUIRE(!(out_nchw || Npad != Cout) || (y && !y_hi && !residual), "conv2d_tc: NCHW / ragged-Cout output is fp32 without residual");
+    const int BW = pick_bw(Wo), BH = 128 / BW;
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     const long long adims[4] = {Cin, W, H, B};
-    const int abox[4] = {BK, BW, BH, 1};
+    const int abox[4] = {BK, BW * stride, BH * stride, 1};
+    const int astr[4] = {1, stride, stride, 1};
     const int taps = ksize * ksize;
-    const long long bdims[3] = {(long long)taps * Cin, Cout, 1};
-    const int BN = (Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32);
+    const long long bdims[3] = {(long long)taps * Cin, Npad, 1};
+    const int BN = (Npad % 128 == 0) ? 128 : ((Npad % 64 == 0) ? 64 : 32);
     const int bbox[3] = {BK, BN, 1};
     int rc;
-    if ((rc = make_map(&a_hi, x_hi, 4, adims, abox)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox)) ||
+    if ((rc = make_map(&a_hi, x_hi, 4, adims, abox, astr)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox, astr)) ||
         (rc = make_map(&b_hi, w_hi, 3, bdims, bbox)) || (rc = make_map(&b_lo, w_lo, 3, bdims, bbox)))
         return rc;
     TcParams p{};
-    p.tiles_x = cdiv(W, BW); p.tiles_y = cdiv(H, BH); p.BW = BW; p.BH = BH; p.Ho = H; p.Wo = W;
-    p.taps = taps; p.ks = ksize; p.pad = ksize / 2; p.kblocks_per_tap = Cin / BK; p.N = Cout; p.nsplit = nsplit;
-    p.a_batched = 1; p.b_batched = 0; p.d_batch_stride = (long long)H * W * Cout; p.alpha = 1.0f;
+    p.tiles_x = cdiv(Wo, BW); p.tiles_y = cdiv(Ho, BH); p.BW = BW; p.BH = BH; p.Ho = Ho; p.Wo = Wo;
+    p.taps = taps; p.ks = ksize; p.pad = (stride == 1) ? ksize / 2 : 0; p.stride = stride; p.kblocks_per_tap = Cin / BK;
+    p.N = out_nchw ? Cout : Npad; p.n_valid = Cout; p.out_nchw = out_nchw; p.nsplit = nsplit;
+    if (!out_nchw && Npad != Cout) p.N = Cout;
+    p.a_batched = 1; p.b_batched = 0; p.d_batch_stride = (long long)Ho * Wo * Cout; p.alpha = 1.0f;
     p.bias_n = bias; p.bias_m = nullptr; p.R = residual; p.D = y; p.D_hi = (__nv_bfloat16 *)y_hi; p.D_lo = (__nv_bfloat16 *)y_lo;
     const int tiles_m = p.tiles_x * p.tiles_y * B;
     cudaStream_t s = (cudaStream_t)stream;
-    if (BN == 128) return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Cout, s);
-    if (BN == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Cout, s);
-    return launch_tc<32>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Cout, s);
+    if (BN == 128) return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, s);
+    if (BN == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, s);
+    return launch_tc<32>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, s);
 }
 
 extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const void *b_hi_p, const void *b_lo_p, const float *bias_m,
@@ -502,7 +558,7 @@ extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const voi
         return rc;
     TcParams p{};
     p.tiles_x = cdiv(M, 128); p.tiles_y = 1; p.BW = 128; p.BH = 1; p.Ho = 1; p.Wo = M;
-    p.taps = 1; p.ks = 1; p.pad = 0; p.kblocks_per_tap = cdiv(K, BK); p.N = N; p.nsplit = nsplit;
+    p.taps = 1; p.ks = 1; p.pad = 0; p.stride = 1; p.kblocks_per_tap = cdiv(K, BK); p.N = N; p.n_valid = N; p.out_nchw = 0; p.nsplit = nsplit;
     p.a_batched = a_batched; p.b_batched = b_batched; p.d_batch_stride = (long long)M * N; p.alpha = alpha;
     p.bias_n = nullptr; p.bias_m = bias_m; p.R = nullptr; p.D = C; p.D_hi = (__nv_bfloat16 *)c_hi; p.D_lo = (__nv_bfloat16 *)c_lo;
     const int tiles_m = p.tiles_x * batch;

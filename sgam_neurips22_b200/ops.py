@@ -248,8 +248,12 @@ def split_bf16(x, upsample=0):
     return hi, lo
 
 
-def split_weight(w):
-    """Host-side one-off split of a weight matrix [N, K] fp32 -> (hi, lo) bf16 (same rounding as the device split)."""
+def split_weight(w, pad_rows_to=1):
+    """Host-side one-off split of a weight matrix [N, K] fp32 -> (hi, lo) bf16 (same rounding as the device split);
+    rows are zero-padded to a multiple of `pad_rows_to` (32 for conv weights: the 4-channel head)."""
+    if pad_rows_to > 1 and w.shape[-2] % pad_rows_to:
+        pad = pad_rows_to - w.shape[-2] % pad_rows_to
+        w = torch.cat([w, w.new_zeros(*w.shape[:-2], pad, w.shape[-1])], dim=-2)
     hi = w.to(torch.bfloat16)
     lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
     return hi.contiguous(), lo.contiguous()
@@ -284,25 +288,27 @@ def tc_supported_conv(H, W, Cin, Cout, ksize, stride):
     return bool(_lib.load().sgam_tc_supported_conv(H, W, Cin, Cout, ksize, stride))
 
 
-def conv2d_tc(x, w, bias, residual=None, ksize=3, out_f32=True, out_split=False, nsplit=3):
-    """Stride-1 conv on tcgen05.  x = (hi, lo) bf16 [B,H,W,Cin]; w = (hi, lo) bf16 [Cout, k*k*Cin]; bias fp32.
-    Returns fp32 y [B,H,W,Cout] and/or the (hi, lo) pair, as requested."""
+def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=False, out_f32=True, out_split=False, nsplit=3):
+    """Conv on tcgen05 (stride 1 symmetric pad, or stride 2 = Downsample).  x = (hi, lo) bf16 [B,H,W,Cin];
+    w = (hi, lo) bf16 [ceil32(Cout), k*k*Cin]; bias fp32 [Cout].  Returns fp32 y [B,Ho,Wo,Cout] (or [B,Cout,Ho,Wo] with
+    out_nchw) and/or the (hi, lo) pair, as requested."""
     lib = _lib.load()
     x_hi, x_lo = x
     w_hi, w_lo = w
     for n, t in (("x_hi", x_hi), ("x_lo", x_lo), ("w_hi", w_hi), ("w_lo", w_lo)):
         _chk(t, torch.bfloat16, n)
     B, H, W, Cin = x_hi.shape
-    Cout = w_hi.shape[0]
-    if w_hi.shape[1] != ksize * ksize * Cin:
-        raise RuntimeError(f"conv2d_tc: weight {tuple(w_hi.shape)} does not match k={ksize} Cin={Cin}")
-    y = torch.empty(B, H, W, Cout, device=x_hi.device) if out_f32 else None
-    pair = _bf16_pair((B, H, W, Cout), x_hi.device) if out_split else (None, None)
+    Cout = w_hi.shape[0] if cout is None else cout
+    if w_hi.shape[1] != ksize * ksize * Cin or w_hi.shape[0] != (Cout + 31) // 32 * 32:
+        raise RuntimeError(f"conv2d_tc: weight {tuple(w_hi.shape)} does not match k={ksize} Cin={Cin} Cout={Cout}")
+    Ho, Wo = H // stride, W // stride
+    y = torch.empty((B, Cout, Ho, Wo) if out_nchw else (B, Ho, Wo, Cout), device=x_hi.device) if out_f32 else None
+    pair = _bf16_pair((B, Ho, Wo, Cout), x_hi.device) if out_split else (None, None)
     if residual is not None:
         _chk(residual, name="residual")
     _lib.check(lib.sgam_conv2d_tc(x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), _ptr(bias),
                                   _ptr(residual), _ptr(y), _ptr(pair[0]), _ptr(pair[1]), B, H, W, Cin, Cout, ksize,
-                                  nsplit, _stream()), "sgam_conv2d_tc")
+                                  stride, int(out_nchw), nsplit, _stream()), "sgam_conv2d_tc")
     if out_f32 and out_split:
         return y, pair
     return y if out_f32 else pair

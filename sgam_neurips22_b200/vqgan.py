@@ -57,9 +57,8 @@ class VQGANEngine:
         self.wsplit = {}
         if self.mode == "tc":
             for k, v in p.items():
-                if k.endswith(".weight") and v.dim() == 2 and k != "quantize.embedding.weight" and v.shape[1] % 64 == 0 \
-                        and v.shape[0] % 32 == 0:
-                    self.wsplit[k[:-len(".weight")]] = ops.split_weight(v)
+                if k.endswith(".weight") and v.dim() == 2 and k != "quantize.embedding.weight" and v.shape[1] % 64 == 0:
+                    self.wsplit[k[:-len(".weight")]] = ops.split_weight(v, pad_rows_to=32)
 
     def has(self, name):
         return f"{name}.weight" in self.p
@@ -79,11 +78,14 @@ class VQGANEngine:
         if self.mode != "tc" or name not in self.wsplit:
             return False
         B, H, W, Cin = x_shape
-        return ops.tc_supported_conv(H, W, Cin, self.p[f"{name}.weight"].shape[0], ksize, stride)
+        if H % stride or W % stride:
+            return False
+        return ops.tc_supported_conv(H // stride, W // stride, Cin, self.p[f"{name}.weight"].shape[0], ksize, stride)
 
     def conv_tc(self, name, xs, ksize, **kw):
         """tcgen05 conv on a split-bf16 activation pair."""
-        return ops.conv2d_tc(xs, self.wsplit[name], self.p[f"{name}.bias"], ksize=ksize, nsplit=self.nsplit, **kw)
+        return ops.conv2d_tc(xs, self.wsplit[name], self.p[f"{name}.bias"], ksize=ksize, nsplit=self.nsplit,
+                             cout=self.p[f"{name}.weight"].shape[0], **kw)
 
     def conv_from_f32(self, name, x, ksize, upsample=0, residual=None):
         """conv of an fp32 activation: split (+ fused x2 up-sampling) then tcgen05, or the fp32 kernel."""
@@ -142,7 +144,11 @@ class VQGANEngine:
                 if self.has(f"encoder.down.{l}.attn.{b}.norm"):
                     h = self.attn_block(f"encoder.down.{l}.attn.{b}", h)
             if l != nres - 1:
-                h = self.conv(f"encoder.down.{l}.downsample.conv", h, ksize=3, stride=2, pad_mode=1)
+                name = f"encoder.down.{l}.downsample.conv"
+                if self.tc_ok(name, h.shape, 3, stride=2):
+                    h = self.conv_tc(name, ops.split_bf16(h), 3, stride=2)
+                else:
+                    h = self.conv(name, h, ksize=3, stride=2, pad_mode=1)
         h = self.resnet_block("encoder.mid.block_1", h)
         h = self.attn_block("encoder.mid.attn_1", h)
         h = self.resnet_block("encoder.mid.block_2", h)
@@ -162,8 +168,10 @@ class VQGANEngine:
                     h = self.attn_block(f"decoder.up.{l}.attn.{b}", h)
             if l != 0:
                 h = self.conv_from_f32(f"decoder.up.{l}.upsample.conv", h, 3, upsample=1)
+        if self.tc_ok("decoder.conv_out", h.shape, 3):                          # Cout = 4: zero-padded to one 32-column tile
+            return self.conv_tc("decoder.conv_out", self.norm_split("decoder.norm_out", h, True), 3, out_nchw=True)
         h = self.norm("decoder.norm_out", h, True)
-        return self.conv("decoder.conv_out", h, ksize=3, out_nchw=True)        # [B, out_ch, H, W]; Cout = 4: fp32 head kernel
+        return self.conv("decoder.conv_out", h, ksize=3, out_nchw=True)        # [B, out_ch, H, W]
 
     # ------------------------------------------------------------------ VQModel pieces
     def encode(self, x, mask=None):

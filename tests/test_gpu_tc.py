@@ -40,9 +40,10 @@ def test_split_producers(ops):
             ref = ref * torch.sigmoid(ref) if swish else ref
             hi, lo = ops.groupnorm_split(x.permute(0, 2, 3, 1).contiguous().cuda(), ga.cuda(), be.cuda(), swish)
             assert rel((hi.float() + lo.float()).permute(0, 3, 1, 2), ref) < 2e-5
-    s = torch.randn(3, 50, 256, generator=g) * 4
-    hi, lo = ops.softmax_split(s.cuda())
-    assert rel(hi.float() + lo.float(), torch.softmax(s.double(), -1)) < 2e-5
+    for cols in (16, 256, 1000, 4096, 5000):
+        s = torch.randn(3, 7, cols, generator=g) * 4
+        hi, lo = ops.softmax_split(s.cuda())
+        assert rel(hi.float() + lo.float(), torch.softmax(s.double(), -1)) < 2e-5, cols
 
 
 @pytest.mark.parametrize("shape", [(1, 128, 128, 64), (2, 384, 256, 192), (1, 16, 32, 16), (2, 200, 96, 72), (1, 4096, 4096, 256)])
@@ -83,7 +84,40 @@ def test_conv2d_tc(ops, case):
     y, (yh, yl) = ops.conv2d_tc(xs, ws, bias.cuda(), residual=r.permute(0, 2, 3, 1).contiguous().cuda(), ksize=ks, out_split=True)
     assert rel(y.permute(0, 3, 1, 2), ref) < 5e-5
     assert rel((yh.float() + yl.float()).permute(0, 3, 1, 2), ref) < 5e-5
-    assert not ops.tc_supported_conv(H, W, 4, Cout, ks, 1) and not ops.tc_supported_conv(H, W, Cin, Cout, ks, 2)
+    assert not ops.tc_supported_conv(H, W, 4, Cout, ks, 1)
+
+
+@pytest.mark.parametrize("case", [(1, 32, 32, 128, 128), (2, 256, 256, 128, 128), (1, 8, 8, 256, 256), (1, 64, 32, 256, 64)])
+def test_conv2d_tc_downsample_stride2(ops, case):
+    """Downsample (model.py:56-75): zero pad right/bottom, 3x3 stride 2, through the strided TMA box."""
+    B, H, W, Cin, Cout = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    ref = F.conv2d(F.pad(x.double(), (0, 1, 0, 1)), w.double(), bias.double(), stride=2)
+    xs = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda())
+    ws = ops.split_weight(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda(), pad_rows_to=32)
+    y = ops.conv2d_tc(xs, ws, bias.cuda(), ksize=3, stride=2, cout=Cout)
+    assert tuple(y.shape) == (B, H // 2, W // 2, Cout)
+    assert rel(y.permute(0, 3, 1, 2), ref) < 5e-5
+
+
+@pytest.mark.parametrize("case", [(1, 32, 32, 128, 4), (2, 256, 256, 128, 4), (1, 16, 16, 128, 20)])
+def test_conv2d_tc_small_cout_head(ops, case):
+    """decoder.conv_out (model.py:503-507): 3x3 conv to 4 channels, zero-padded to one 32-column tile, NCHW output."""
+    B, H, W, Cin, Cout = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    xs = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda())
+    ws = ops.split_weight(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda(), pad_rows_to=32)
+    y = ops.conv2d_tc(xs, ws, bias.cuda(), ksize=3, cout=Cout, out_nchw=True)
+    assert tuple(y.shape) == (B, Cout, H, W) and rel(y, ref) < 5e-5
+    y2 = ops.conv2d_tc(xs, ws, bias.cuda(), ksize=3, cout=Cout)
+    assert tuple(y2.shape) == (B, H, W, Cout) and rel(y2.permute(0, 3, 1, 2), ref) < 5e-5
 
 
 @pytest.fixture(scope="module")
