@@ -165,7 +165,15 @@ int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int strid
  * Output fp32 y (NHWC, or [B,Cout,Ho,Wo] when out_nchw: the decoder head) and/or split-bf16 y_hi/y_lo. */
 int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                    const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
-                   int ksize, int stride, int out_nchw, int nsplit, void *stream);
+                   int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, void *stream);
+
+/* GroupNorm statistics fused into the conv epilogue: when gn_partial (sgam_tc_gn_partial_floats(B,Ho,Wo) floats) is
+ * passed to sgam_conv2d_tc, each pixel block writes the per-group sum / sum of squares of the finished output, and
+ * sgam_groupnorm_split_fused finalises them (fp64) and applies GroupNorm(32,C,eps=1e-6) (+ swish) -> split bf16
+ * without re-reading the tensor for statistics. */
+long long sgam_tc_gn_partial_floats(int B, int Ho, int Wo);
+int sgam_groupnorm_split_fused(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
+                               float *gn_partial, int B, int Ho, int Wo, int C, int swish, void *stream);
 
 /* Batched C = alpha * A . B^T (+ bias_m[row]) on tensor cores.  A [batch|1, M, K], B [batch|1, N, K] split-bf16
  * (a_batched / b_batched say whether the operand has the batch dimension); output fp32 C and/or split-bf16. */

@@ -91,13 +91,22 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
 // ------------------------------------------------------------------------------------------------ the GEMM kernel
 constexpr int BM = 128, BK = 64, STAGES = 3, TC_THREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KB
 
 struct TcParams {
-    // tiling of M: tile t -> (b, ty, tx); rows of the tile are (ly, lx) with lx < BW, ly < BH, BW*BH = 128
+    // tiling of M: m-tile -> (b, ty, tx); rows of the tile are (ly, lx) with lx < BW, ly < BH, BW*BH = 128
     int tiles_x, tiles_y, BW, BH;
+    int tiles_m, tiles_n;       // persistent schedule: tile id = m_tile * tiles_n + n_tile (the n-tiles of one pixel block
+                                // run on neighbouring SMs at the same time, so the A box is fetched from HBM once)
     int Ho, Wo;                 // output pixel grid per batch element (plain GEMM: Ho = 1, Wo = M)
     int taps, ks, pad, stride;  // conv: ks*ks taps, left/top pad, stride; plain GEMM: taps = 1, ks = 1, pad = 0, stride = 1
     int kblocks_per_tap;        // C / 64 (rounded up)
@@ -111,7 +120,29 @@ struct TcParams {
     const float *bias_n, *bias_m, *R;
     float *D;                   // fp32 output (or null)
     __nv_bfloat16 *D_hi, *D_lo; // split-bf16 output (or null)
+    float *stats;               // or null: per-(batch, pixel-block) GroupNorm partial sums [B][tiles_y*tiles_x][32][2]
+    int cpg;                    // channels per group = N / 32 when stats != null
 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// per-warp GroupNorm partial sums of one 32-column chunk: CPG channels per group, rows = lanes
+template <int CPG>
+__device__ __forceinline__ void chunk_group_sums(const float (&o)[32], bool row_ok, int lane, float *dst /* [32/CPG][2] */) {
+    constexpr int G = 32 / CPG;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPG; ++j) { const float v = row_ok ? o[g * CPG + j] : 0.f; s += v; q = fmaf(v, v, q); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); q += __shfl_xor_sync(0xffffffffu, q, off); }
+        if (lane == 0) { dst[2 * g] = s; dst[2 * g + 1] = q; }
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -119,26 +150,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams p) {
     constexpr int B_TILE_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;        // two accumulator buffers
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024-B alignment
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float stat_s[4][BN / 4 * 2];        // [epilogue warp][group in tile][sum, sumsq]  (cpg >= 4)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tx = t % p.tiles_x; t /= p.tiles_x;
-    const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
-    const int n0 = blockIdx.y * BN;
     const int num_kb = p.taps * p.kblocks_per_tap;
+    const int total_tiles = p.tiles_m * p.tiles_n;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // one full warp allocates BN TMEM columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(BN) : "memory");
+    if (warp == 1) {   // one full warp allocates the TMEM columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -150,20 +179,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         // ===== TMA producer =====
         if (lane == 0) {
             const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_TILE_BYTES + B_TILE_BYTES);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES, it = kb / STAGES;
-                mbar_wait(&empty_bar[s], (it & 1) ^ 1);
-                uint8_t *st = smem + (size_t)s * STAGE_BYTES;
-                const int tap = kb / p.kblocks_per_tap, kc = kb - tap * p.kblocks_per_tap;
-                const int kh = tap / p.ks, kw = tap - kh * p.ks;
-                const int cx = tx * p.BW * p.stride + kw - p.pad, cy = ty * p.BH * p.stride + kh - p.pad;
+            int kbg = 0;                                              // k-block counter across tiles (ring position)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.tiles_n) * BN;
+                int t = tile / p.tiles_n;
+                const int tx = t % p.tiles_x; t /= p.tiles_x;
+                const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
                 const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-                mbar_expect_tx(&full_bar[s], tx_bytes);
-                tma_load_4d(st, &mapA_hi, &full_bar[s], kc * BK, cx, cy, ab);
-                tma_load_3d(st + 2 * A_TILE_BYTES, &mapB_hi, &full_bar[s], kb * BK, n0, bb);
-                if (p.nsplit == 3) {
-                    tma_load_4d(st + A_TILE_BYTES, &mapA_lo, &full_bar[s], kc * BK, cx, cy, ab);
-                    tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapB_lo, &full_bar[s], kb * BK, n0, bb);
+                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+                    const int s = kbg % STAGES, it = kbg / STAGES;
+                    mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+                    uint8_t *st = smem + (size_t)s * STAGE_BYTES;
+                    const int tap = kb / p.kblocks_per_tap, kc = kb - tap * p.kblocks_per_tap;
+                    const int kh = tap / p.ks, kw = tap - kh * p.ks;
+                    const int cx = tx * p.BW * p.stride + kw - p.pad, cy = ty * p.BH * p.stride + kh - p.pad;
+                    mbar_expect_tx(&full_bar[s], tx_bytes);
+                    tma_load_4d(st, &mapA_hi, &full_bar[s], kc * BK, cx, cy, ab);
+                    tma_load_3d(st + 2 * A_TILE_BYTES, &mapB_hi, &full_bar[s], kb * BK, n0, bb);
+                    if (p.nsplit == 3) {
+                        tma_load_4d(st + A_TILE_BYTES, &mapA_lo, &full_bar[s], kc * BK, cx, cy, ab);
+                        tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapB_lo, &full_bar[s], kb * BK, n0, bb);
+                    }
                 }
             }
         }
@@ -171,101 +207,133 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES, it = kb / STAGES;
-                mbar_wait(&full_bar[s], it & 1);
+            int kbg = 0, li = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+                const int acc = li & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((li >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 tc_fence_after();
-                uint8_t *st = smem + (size_t)s * STAGE_BYTES;
-                const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_TILE_BYTES);
-                const uint64_t b_hi = make_smem_desc(st + 2 * A_TILE_BYTES), b_lo = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+                    const int s = kbg % STAGES, it = kbg / STAGES;
+                    mbar_wait(&full_bar[s], it & 1);
+                    tc_fence_after();
+                    uint8_t *st = smem + (size_t)s * STAGE_BYTES;
+                    const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_TILE_BYTES);
+                    const uint64_t b_hi = make_smem_desc(st + 2 * A_TILE_BYTES), b_lo = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {            // UMMA_K = 16 bf16 = 32 B: advance the start address field by 2
-                    const uint64_t off = (uint64_t)(k * 2);
-                    umma_bf16(tmem_base, a_hi + off, b_hi + off, idesc, (kb | k) ? 1u : 0u);
-                    if (p.nsplit == 3) {
-                        umma_bf16(tmem_base, a_hi + off, b_lo + off, idesc, 1u);
-                        umma_bf16(tmem_base, a_lo + off, b_hi + off, idesc, 1u);
+                    for (int k = 0; k < BK / 16; ++k) {            // UMMA_K = 16 bf16 = 32 B: advance the start address field by 2
+                        const uint64_t off = (uint64_t)(k * 2);
+                        umma_bf16(tmem_d, a_hi + off, b_hi + off, idesc, (kb | k) ? 1u : 0u);
+                        if (p.nsplit == 3) {
+                            umma_bf16(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
+                            umma_bf16(tmem_d, a_lo + off, b_hi + off, idesc, 1u);
+                        }
                     }
+                    umma_commit(&empty_bar[s]);                     // frees the stage when these MMAs retire
                 }
-                umma_commit(&empty_bar[s]);                     // frees the stage when these MMAs retire
+                umma_commit(&tmem_full_bar[acc]);                   // accumulator complete
             }
-            umma_commit(&tmem_full_bar);                        // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4).. =====
         const int q = warp & 3;
         const int r = q * 32 + lane;                           // tile row = TMEM lane
         const int ly = r / p.BW, lx = r - ly * p.BW;
-        const int oy = ty * p.BH + ly, ox = tx * p.BW + lx;
-        const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
-        const long long m = (long long)oy * p.Wo + ox;          // row within the batch slice
-        const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-        const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
+        int li = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+            const int acc = li & 1;
+            const int n0 = (tile % p.tiles_n) * BN;
+            int t = tile / p.tiles_n;
+            const int m_tile = t % (p.tiles_x * p.tiles_y);
+            const int tx = t % p.tiles_x; t /= p.tiles_x;
+            const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
+            const int oy = ty * p.BH + ly, ox = tx * p.BW + lx;
+            const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
+            const long long m = (long long)oy * p.Wo + ox;          // row within the batch slice
+            const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
+            const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
+            mbar_wait(&tmem_full_bar[acc], (li >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (!row_ok) continue;
-            const int n = n0 + c0;
-            if (n >= p.n_valid) continue;
-            float o[32];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                const int n = n0 + c0;
+                if (n >= p.n_valid) continue;
+                float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bm;
-            if (p.out_nchw || n + 32 > p.n_valid) {      // ragged / NCHW tail (the 4-channel head): scalar stores, coalesced over ox
+                for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bm;
+                if (p.out_nchw || n + 32 > p.n_valid) {      // ragged / NCHW tail (the 4-channel head): scalar stores, coalesced over ox
+                    if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (n + j < p.n_valid) {
-                        float val = o[j] + (p.bias_n ? __ldg(p.bias_n + n + j) : 0.0f);
-                        if (p.out_nchw) p.D[(((long long)b * p.n_valid + n + j) * p.Ho + oy) * p.Wo + ox] = val;
-                        else p.D[row_off + n + j] = val + (p.R ? __ldg(p.R + row_off + n + j) : 0.0f);
+                        for (int j = 0; j < 32; ++j) {
+                            if (n + j < p.n_valid) {
+                                float val = o[j] + (p.bias_n ? __ldg(p.bias_n + n + j) : 0.0f);
+                                if (p.out_nchw) p.D[(((long long)b * p.n_valid + n + j) * p.Ho + oy) * p.Wo + ox] = val;
+                                else p.D[row_off + n + j] = val + (p.R ? __ldg(p.R + row_off + n + j) : 0.0f);
+                            }
+                        }
+                    }
+                    continue;
+                }
+                if (p.bias_n) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias_n + n + j));
+                        o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
                     }
                 }
-                continue;
-            }
-            if (p.bias_n) {
+                if (p.R && row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias_n + n + j));
-                    o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.R + row_off + n + j));
+                        o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+                    }
+                }
+                if (p.stats) {                                // GroupNorm statistics of the finished output, per warp
+                    float *dst = &stat_s[q][(c0 / p.cpg) * 2];
+                    if (p.cpg == 4) chunk_group_sums<4>(o, row_ok, lane, dst);
+                    else if (p.cpg == 8) chunk_group_sums<8>(o, row_ok, lane, dst);
+                    else chunk_group_sums<16>(o, row_ok, lane, dst);
+                }
+                if (!row_ok) continue;
+                if (p.D) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(p.D + row_off + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                }
+                if (p.D_hi) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) split2(o[j], o[j + 1], hi[j / 2], lo[j / 2]);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        *reinterpret_cast<uint4 *>(p.D_hi + row_off + n + 2 * j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+                        *reinterpret_cast<uint4 *>(p.D_lo + row_off + n + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                    }
                 }
             }
-            if (p.R) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.R + row_off + n + j));
-                    o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+            // this accumulator buffer may be overwritten by the MMA warp as soon as all four warps have read it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (p.stats) {
+                epilogue_bar_sync();
+                const int e = threadIdx.x - 64;                     // 0..127
+                const int nvals = (BN / p.cpg) * 2;
+                if (e < nvals) {
+                    const float v = (stat_s[0][e] + stat_s[1][e]) + (stat_s[2][e] + stat_s[3][e]);
+                    const int g = n0 / p.cpg + (e >> 1);
+                    p.stats[(((long long)b * (p.tiles_x * p.tiles_y) + m_tile) * 32 + g) * 2 + (e & 1)] = v;
                 }
-            }
-            if (p.D) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4 *>(p.D + row_off + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            }
-            if (p.D_hi) {
-                uint32_t hi[16], lo[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(o[j]), h1 = __float2bfloat16_rn(o[j + 1]);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(o[j] - __bfloat162float(h0));
-                    const __nv_bfloat16 l1 = __float2bfloat16_rn(o[j + 1] - __bfloat162float(h1));
-                    hi[j / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[j / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    *reinterpret_cast<uint4 *>(p.D_hi + row_off + n + 2 * j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
-                    *reinterpret_cast<uint4 *>(p.D_lo + row_off + n + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
-                }
+                epilogue_bar_sync();
             }
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -304,8 +372,19 @@ int make_map(CUtensorMap *m, const void *base, int rank, const long long *dims, 
     return SGAM_OK;
 }
 
+int sm_count_cached() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN>
-int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, const TcParams &p,
+int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, TcParams p,
               int tiles_m, int N, cudaStream_t s) {
     constexpr size_t smem = (size_t)STAGES * (2 * A_TILE_BYTES + 2 * BN * BK * 2) + 1024;
     static bool configured = false;
@@ -313,20 +392,16 @@ int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMa
         SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid(tiles_m, cdiv(N, BN));
+    p.tiles_m = tiles_m;
+    p.tiles_n = cdiv(N, BN);
+    const int total = p.tiles_m * p.tiles_n;
+    const int grid = total < sm_count_cached() ? total : sm_count_cached();      // persistent: one CTA per SM
     tc_gemm_kernel<BN><<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, p);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ producers of split bf16
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-}
-
 // x fp32 [B, H, W, C] -> hi / lo bf16 [B, H<<up, W<<up, C] (nearest x2 up-sampling fused when up = 1)
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
@@ -352,12 +427,14 @@ split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, _
 
 // GroupNorm apply (+ swish) with split-bf16 output; statistics come from gn_stats (net_simt.cu) partials
 __global__ void __launch_bounds__(256)
-gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ gamma,
-                      const float *__restrict__ beta, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
-                      long long HW, int C, int S, int swish) {
+gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ meanrstd,
+                      const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ hi,
+                      __nv_bfloat16 *__restrict__ lo, long long HW, int C, int S, int swish) {
     __shared__ float mean_s[32], rstd_s[32];
     const int b = blockIdx.y, tid = threadIdx.x;
-    if (tid < 32) {
+    if (meanrstd) {                     // statistics already finalised (fused into the producing conv's epilogue)
+        if (tid < 32) { mean_s[tid] = meanrstd[(b * 32 + tid) * 2]; rstd_s[tid] = meanrstd[(b * 32 + tid) * 2 + 1]; }
+    } else if (tid < 32) {
         double a = 0.0, q = 0.0;
         for (int s = 0; s < S; ++s) {
             const double *src = partial + (((size_t)b * S + s) * 32 + tid) * 2;
@@ -451,6 +528,28 @@ softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi
     }
 }
 
+// reduce the per-pixel-block partial sums written by tc_gemm_kernel's epilogue: [B][tiles][32][2] fp32 -> mean, rstd
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrstd, int tiles, double count) {
+    __shared__ double red[8][32][2];
+    const int b = blockIdx.x, g = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double a = 0.0, q = 0.0;
+    for (int t = w; t < tiles; t += 8) {
+        const float2 v = *reinterpret_cast<const float2 *>(partial + (((size_t)b * tiles + t) * 32 + g) * 2);
+        a += (double)v.x; q += (double)v.y;
+    }
+    red[w][g][0] = a; red[w][g][1] = q;
+    __syncthreads();
+    if (w == 0) {
+        for (int k = 1; k < 8; ++k) { a += red[k][g][0]; q += red[k][g][1]; }
+        const double mean = a / count;
+        double var = q / count - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        meanrstd[(b * 32 + g) * 2] = (float)mean;
+        meanrstd[(b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-6));
+    }
+}
+
 }  // namespace
 
 // gn_stats launcher lives in net_simt.cu
@@ -474,8 +573,32 @@ extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const fl
     if (rc) return rc;
     const long long total = HW * (C / 4);
     const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
-    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, partial, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
+    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
                                                           sgam_gn_splits(HW), swish);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+extern "C" long long sgam_tc_gn_partial_floats(int B, int Ho, int Wo) {
+    const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
+    const long long tiles = (long long)cdiv(Wo, BW) * cdiv(Ho, BH);
+    return (long long)B * tiles * 64 + (long long)B * 64;           // partial sums, then [B][32][mean, rstd]
+}
+
+extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
+                                          float *gn_partial, int B, int Ho, int Wo, int C, int swish, void *stream) {
+    SGAM_REQUIRE(x && gamma && beta && hi && lo && gn_partial, "groupnorm_split_fused: null pointer");
+    SGAM_REQUIRE(B > 0 && Ho > 0 && Wo > 0 && C % 128 == 0 && C <= 512, "groupnorm_split_fused: C=%d must be 128, 256, 384 or 512", C);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
+    const int tiles = cdiv(Wo, BW) * cdiv(Ho, BH);
+    const long long HW = (long long)Ho * Wo;
+    float *meanrstd = gn_partial + (long long)B * tiles * 64;
+    gn_finalize_kernel<<<B, 256, 0, s>>>(gn_partial, meanrstd, tiles, (double)HW * (C / 32));
+    SGAM_LAUNCH_OK();
+    const long long total = HW * (C / 4);
+    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
+    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
@@ -504,8 +627,9 @@ extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize
 
 extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                               const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
-                              int ksize, int stride, int out_nchw, int nsplit, void *stream) {
+                              int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, void *stream) {
     SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && (y || (y_hi && y_lo)), "conv2d_tc: null pointer");
+    SGAM_REQUIRE(!gn_partial || (Cout % 128 == 0 && Cout <= 512 && !out_nchw), "conv2d_tc: fused GroupNorm statistics need Cout in {128,256,384,512}");
     SGAM_REQUIRE(stride == 1 || stride == 2, "conv2d_tc: stride %d", stride);
     const int Ho = H / stride, Wo = W / stride;        // stride 1: same; stride 2: pad (0,1,0,1) then 3x3/2 -> H/2 (even H)
     SGAM_REQUIRE(H % stride == 0 && W % stride == 0, "conv2d_tc: odd extent with stride 2");
@@ -533,6 +657,7 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
     if (!out_nchw && Npad != Cout) p.N = Cout;
     p.a_batched = 1; p.b_batched = 0; p.d_batch_stride = (long long)Ho * Wo * Cout; p.alpha = 1.0f;
     p.bias_n = bias; p.bias_m = nullptr; p.R = residual; p.D = y; p.D_hi = (__nv_bfloat16 *)y_hi; p.D_lo = (__nv_bfloat16 *)y_lo;
+    p.stats = gn_partial; p.cpg = Cout / 32;
     const int tiles_m = p.tiles_x * p.tiles_y * B;
     cudaStream_t s = (cudaStream_t)stream;
     if (BN == 128) return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, s);
@@ -561,6 +686,7 @@ extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const voi
     p.taps = 1; p.ks = 1; p.pad = 0; p.stride = 1; p.kblocks_per_tap = cdiv(K, BK); p.N = N; p.n_valid = N; p.out_nchw = 0; p.nsplit = nsplit;
     p.a_batched = a_batched; p.b_batched = b_batched; p.d_batch_stride = (long long)M * N; p.alpha = alpha;
     p.bias_n = nullptr; p.bias_m = bias_m; p.R = nullptr; p.D = C; p.D_hi = (__nv_bfloat16 *)c_hi; p.D_lo = (__nv_bfloat16 *)c_lo;
+    p.stats = nullptr; p.cpg = 0;
     const int tiles_m = p.tiles_x * batch;
     cudaStream_t s = (cudaStream_t)stream;
     if (BN == 128) return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, N, s);

@@ -265,9 +265,15 @@ def groupnorm_split(x, gamma, beta, swish, workspace=None):
     _chk(x, name="x"), _chk(gamma, name="gamma"), _chk(beta, name="beta")
     B, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * C)
+    hi, lo = _bf16_pair(tuple(x.shape), x.device)
+    partial = getattr(x, "gn_partial", None)
+    if partial is not None and x.dim() == 4:
+        _lib.check(lib.sgam_groupnorm_split_fused(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+                                                  partial.data_ptr(), B, x.shape[1], x.shape[2], C, int(swish), _stream()),
+                   "sgam_groupnorm_split_fused")
+        return hi, lo
     if workspace is None:
         workspace = torch.empty(B * lib.sgam_gn_splits(HW) * 64, dtype=torch.float64, device=x.device)
-    hi, lo = _bf16_pair(tuple(x.shape), x.device)
     _lib.check(lib.sgam_groupnorm_split(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), hi.data_ptr(), lo.data_ptr(),
                                         workspace.data_ptr(), B, HW, C, int(swish), _stream()), "sgam_groupnorm_split")
     return hi, lo
@@ -288,7 +294,8 @@ def tc_supported_conv(H, W, Cin, Cout, ksize, stride):
     return bool(_lib.load().sgam_tc_supported_conv(H, W, Cin, Cout, ksize, stride))
 
 
-def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=False, out_f32=True, out_split=False, nsplit=3):
+def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=False, out_f32=True, out_split=False, nsplit=3,
+              gn_stats=False):
     """Conv on tcgen05 (stride 1 symmetric pad, or stride 2 = Downsample).  x = (hi, lo) bf16 [B,H,W,Cin];
     w = (hi, lo) bf16 [ceil32(Cout), k*k*Cin]; bias fp32 [Cout].  Returns fp32 y [B,Ho,Wo,Cout] (or [B,Cout,Ho,Wo] with
     out_nchw) and/or the (hi, lo) pair, as requested."""
@@ -306,9 +313,14 @@ def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=
     pair = _bf16_pair((B, Ho, Wo, Cout), x_hi.device) if out_split else (None, None)
     if residual is not None:
         _chk(residual, name="residual")
+    partial = None
+    if gn_stats and out_f32 and not out_nchw and Cout % 128 == 0 and Cout <= 512:
+        partial = torch.empty(lib.sgam_tc_gn_partial_floats(B, Ho, Wo), device=x_hi.device)
     _lib.check(lib.sgam_conv2d_tc(x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), _ptr(bias),
                                   _ptr(residual), _ptr(y), _ptr(pair[0]), _ptr(pair[1]), B, H, W, Cin, Cout, ksize,
-                                  stride, int(out_nchw), nsplit, _stream()), "sgam_conv2d_tc")
+                                  stride, int(out_nchw), nsplit, _ptr(partial), _stream()), "sgam_conv2d_tc")
+    if partial is not None:
+        y.gn_partial = partial          # GroupNorm statistics of y, fused into the epilogue (consumed by groupnorm_split)
     if out_f32 and out_split:
         return y, pair
     return y if out_f32 else pair

@@ -84,6 +84,7 @@ class VQGANEngine:
 
     def conv_tc(self, name, xs, ksize, **kw):
         """tcgen05 conv on a split-bf16 activation pair."""
+        kw.setdefault("gn_stats", True)       # nearly every fp32 conv output feeds a GroupNorm: fuse its statistics
         return ops.conv2d_tc(xs, self.wsplit[name], self.p[f"{name}.bias"], ksize=ksize, nsplit=self.nsplit,
                              cout=self.p[f"{name}.weight"].shape[0], **kw)
 

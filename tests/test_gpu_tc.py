@@ -173,3 +173,28 @@ def test_tc_full_step_256(golden, engines, ds):
     assert rel(pre.permute(0, 3, 1, 2), golden[f"step256.{ds}.pre_quant"]) < 1e-3
     assert rel(dec[:, :, ::4, ::4], golden[f"step256.{ds}.dec_sub"]) < 1e-3
     print(ds, "pre rel", rel(pre.permute(0, 3, 1, 2), golden[f"step256.{ds}.pre_quant"]), "dec rel", rel(dec[:, :, ::4, ::4], golden[f"step256.{ds}.dec_sub"]))
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 128, 128), (1, 64, 64, 128, 256), (3, 8, 8, 256, 512), (1, 256, 256, 128, 128)])
+def test_groupnorm_statistics_fused_into_conv_epilogue(ops, case):
+    """The persistent GEMM's epilogue emits per-pixel-block group sums; groupnorm_split consumes them instead of
+    re-reading the tensor.  Must equal GroupNorm of the conv output."""
+    B, H, W, Cin, Cout = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    bias = torch.randn(Cout, generator=g) * 2
+    r = torch.randn(B, Cout, H, W, generator=g)
+    ga, be = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    conv = F.conv2d(x.double(), w.double(), bias.double(), padding=1) + r.double()
+    ref = F.group_norm(conv, 32, ga.double(), be.double(), eps=1e-6)
+    ref = ref * torch.sigmoid(ref)
+    xs = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda())
+    ws = ops.split_weight(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda(), pad_rows_to=32)
+    y = ops.conv2d_tc(xs, ws, bias.cuda(), residual=r.permute(0, 2, 3, 1).contiguous().cuda(), ksize=3, gn_stats=True)
+    assert hasattr(y, "gn_partial")
+    hi, lo = ops.groupnorm_split(y, ga.cuda(), be.cuda(), True)
+    assert rel((hi.float() + lo.float()).permute(0, 3, 1, 2), ref) < 5e-5
+    y2 = y.clone()                                             # no fused statistics attached: the stats kernel path
+    hi2, lo2 = ops.groupnorm_split(y2, ga.cuda(), be.cuda(), True)
+    assert rel(hi2.float() + lo2.float(), hi.float() + lo.float()) < 1e-5
