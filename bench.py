@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="independent trajectories per GPU (BASELINE.json configs[3]: 64 over 8 GPUs)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-gemm", default=None, help="write the per-launch table of the tensor-core GEMMs of one step to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -268,7 +269,8 @@ def main():
             e0.record()
             y = fn(*a, **kw)
             e1.record()
-            gemm_events.append((e0, e1, flops_of(a, kw, y)))
+            shp = tuple(a[0][0].shape) + tuple((a[1][0] if isinstance(a[1], tuple) else a[1]).shape)
+            gemm_events.append((e0, e1, flops_of(a, kw, y), fn.__name__, shp, {k: v for k, v in kw.items() if isinstance(v, (int, float, bool))}))
             return y
         return wrapper
 
@@ -296,8 +298,14 @@ def main():
     finally:
         for name, (fn, fl) in patched.items():
             setattr(ops, name, fn)
-    conv_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
-    conv_flops_total = sum(f for _, _, f in gemm_events)
+    conv_ms = sum(ev[0].elapsed_time(ev[1]) for ev in gemm_events)
+    conv_flops_total = sum(ev[2] for ev in gemm_events)
+    if args.dump_gemm and rank == 0:
+        with open(args.dump_gemm, "w") as f:
+            f.write("op\tshape(A|B)\tkw\tGFLOP\tms\tTFLOP/s(algorithmic)\n")
+            for ev in gemm_events:
+                t = ev[0].elapsed_time(ev[1])
+                f.write(f"{ev[3]}\t{ev[4]}\t{ev[5]}\t{ev[2] / 1e9:.2f}\t{t:.4f}\t{ev[2] / t / 1e9:.1f}\n")
     conv_tflops = conv_flops_total / (conv_ms * 1e-3) / 1e12
     nsplit = eng.nsplit if eng.mode == "tc" else 1
 

@@ -618,6 +618,17 @@ extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long 
 
 static int pick_bw(int W) { return W >= 128 ? 128 : W; }
 
+// Column-tile width: 128 unless the grid would leave most of the 148 SMs idle, in which case 64-wide tiles double
+// the tile count (tcgen05 runs N=64 at the same MAC rate).  Cost model: waves * (BN + fixed per-tile overhead).
+static int pick_bn(int tiles_m, int N) {
+    if (N % 64) return 32;
+    if (N % 128) return 64;
+    const int sms = sm_count_cached();
+    const long long t128 = (long long)tiles_m * (N / 128), t64 = (long long)tiles_m * (N / 64);
+    const long long c128 = ((t128 + sms - 1) / sms) * (128 + 32), c64 = ((t64 + sms - 1) / sms) * (64 + 32);
+    return c64 < c128 ? 64 : 128;
+}
+
 extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int stride) {
     // H, W: OUTPUT grid.  stride 2 is the Downsample (pad right/bottom, model.py:68-72).
     const bool pow2 = (W & (W - 1)) == 0;
@@ -644,7 +655,7 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
     const int astr[4] = {1, stride, stride, 1};
     const int taps = ksize * ksize;
     const long long bdims[3] = {(long long)taps * Cin, Npad, 1};
-    const int BN = (Npad % 128 == 0) ? 128 : ((Npad % 64 == 0) ? 64 : 32);
+    const int BN = pick_bn(cdiv(Wo, BW) * cdiv(Ho, BH) * B, Npad);
     const int bbox[3] = {BK, BN, 1};
     int rc;
     if ((rc = make_map(&a_hi, x_hi, 4, adims, abox, astr)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox, astr)) ||
@@ -675,7 +686,7 @@ extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const voi
     const long long adims[4] = {K, M, 1, a_batched ? batch : 1};
     const int abox[4] = {BK, 128, 1, 1};
     const long long bdims[3] = {K, N, b_batched ? batch : 1};
-    const int BN = (N % 128 == 0) ? 128 : ((N % 64 == 0) ? 64 : 32);
+    const int BN = pick_bn(cdiv(M, 128) * batch, N);
     const int bbox[3] = {BK, BN, 1};
     int rc;
     if ((rc = make_map(&a_hi, a_hi_p, 4, adims, abox)) || (rc = make_map(&a_lo, a_lo_p, 4, adims, abox)) ||

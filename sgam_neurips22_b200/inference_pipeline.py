@@ -47,6 +47,28 @@ def write_ply(path, xyz, rgb):
         rec.tofile(f)
 
 
+def forward_splat_depth(pipe, src_nodes, T_tgt):
+    """An Open3D-free `tsdf_depth_fn`: the target depth is the z-buffered (nearest-depth) forward splat of the
+    selected source frames with 3x3 hole fill -- the same fused kernel as stage (i) with SGAM_SPLAT_ZMIN.  It stands
+    in for ScalableTSDFVolume + mesh rendering (inference_pipeline.py:745-838) where Open3D is unavailable; it is NOT
+    numerically equivalent to TSDF fusion (that depth is parity-unpinned)."""
+    dev = pipe.device
+    frames = [pipe._frames[tuple(n["grid_coord"])] for n in src_nodes]
+    rgb = torch.stack([f[0] for f in frames])[None].contiguous()
+    dm = torch.stack([f[1] for f in frames])[None].contiguous()
+    N = len(src_nodes)
+    K = torch.from_numpy(pipe.K.astype(np.float32))
+    T = torch.eye(4).repeat(1, N, 1, 1)
+    for i, n in enumerate(src_nodes):
+        T_src = np.eye(4)
+        T_src[:3, :3], T_src[:3, 3] = n["R"], n["t"]
+        T[0, i] = torch.from_numpy((T_tgt @ np.linalg.inv(T_src)).astype(np.float32))
+    Kinv = K.inverse()[None, None].repeat(1, N, 1, 1).contiguous()
+    out = ops.splat_forward(rgb, dm, K[None].to(dev), Kinv.to(dev), T.to(dev), pipe.data, channels_last=True,
+                            policy=ops.SPLAT_ZMIN, want_merge_depth=True)
+    return out["merge_depth"][0, 0]
+
+
 class InfiniteSceneGeneration:
 
     def __init__(self,
@@ -331,7 +353,7 @@ class InfiniteSceneGeneration:
             x, topk=self.topk, extrapolation_mask=extrapolation_mask, get_pre_quantized_feature=True,
             get_quantized_feature=True, sample_number=1)
         x_sample_dets = x_sample_dets[0]                                                      # sample number is 1
-        rgb_u8, depth, src_rgb = ops.frame_outputs(x_sample_dets[:1].contiguous(), self.data, want_src_rgb=True)
+        rgb_u8, depth, src_rgb = ops.frame_outputs(x_sample_dets[0][:1].contiguous(), self.data, want_src_rgb=True)
         self._frames[tuple(tgt_pose_grid_coord)] = (src_rgb[0], depth[0])                     # stays on the device
         if save_res_to_disk:
             self.save_to_disk(tgt_pose_grid_coord, rgb_u8[0].cpu().numpy(), depth[0].cpu().numpy())
