@@ -323,6 +323,39 @@ def main():
     vq_flops = 2.0 * Tk * eng.n_embed * D
     del step_in_x
 
+    # ---------------- single-trajectory latency (batch 1: the reference's own operating point) ---------------------------
+    single = None
+    if B != 1:
+        b1 = {k: v[:1].contiguous() for k, v in host.items()}
+        s_rgb, s_dep = b1["src_imgs"].to(dev), b1["src_depths"].to(dev)
+        s_Kinv, s_Kt, s_T = Kinv[:1].contiguous(), K_tgt[:1].contiguous(), T[:1].contiguous()
+        s_ws = torch.empty(res * res, dtype=torch.int64, device=dev)
+        s_out_rgb = torch.empty(1, res, res, 3, dtype=torch.uint8, device=dev)
+        s_out_depth = torch.empty(1, res, res, device=dev)
+
+        def step_single():
+            s = ops.splat_forward(s_rgb, s_dep, s_Kt, s_Kinv, s_T, ds, channels_last=True, workspace=s_ws)
+            dec, _, _, _ = eng.forward(s["x"], s["mask"])
+            ops.frame_outputs(dec, ds, rgb_u8=s_out_rgb, depth=s_out_depth)
+
+        run_single = step_single
+        step_single()
+        if not args.no_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_single()
+            torch.cuda.current_stream().wait_stream(side)
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                step_single()
+            run_single = g1.replay
+        for _ in range(args.warmup):
+            run_single()
+        ms1 = time_steps(run_single, args.steps, world)
+        single = {"value": world * args.steps / (ms1 / 1000.0), "unit": UNIT, "ms_per_frame": ms1 / args.steps,
+                  "note": "one trajectory per GPU (batch 1), inputs resident, CUDA graph"}
+
     # ---------------- final map all-gather (the only collective; outside the frames/sec region) ----------------------
     poses = torch.zeros(B, 12, dtype=torch.float64)
     ag_ms = None
@@ -358,6 +391,8 @@ def main():
                        "fp32_tflops": vq_flops / (vq_ms * 1e-3) / 1e12},
                 "tc_gemm_ms_per_step": conv_ms},
         }
+        if single is not None:
+            line["single_trajectory"] = single
         if ag_ms is not None:
             line["allgather_ms"] = ag_ms
             line["allgather_bytes_per_rank"] = int(B * sdist.record_bytes(res, res))

@@ -198,3 +198,21 @@ def test_groupnorm_statistics_fused_into_conv_epilogue(ops, case):
     y2 = y.clone()                                             # no fused statistics attached: the stats kernel path
     hi2, lo2 = ops.groupnorm_split(y2, ga.cuda(), be.cuda(), True)
     assert rel(hi2.float() + lo2.float(), hi.float() + lo.float()) < 1e-5
+
+
+def test_tc_network_512_config5_shape(engines, state_dicts):
+    """BASELINE.json configs[4] shape: GoogleEarth at 512x512 (latent 32x32 = 1024 tokens, attention over 16384 tokens),
+    which the reference cannot run unpatched (hard-coded 256 / (16,16): SURVEY.md section 5).  Engine vs the oracle."""
+    from oracle import model as omodel
+    ds = "google_earth"
+    rng = np.random.default_rng(77)
+    xin = rng.uniform(-1, 1, (1, 4, 512, 512)).astype(np.float32)
+    mk = (rng.random((1, 1, 512, 512)) < 0.2)
+    dec_o, pre_o, zq_o, idx_o = omodel.forward(state_dicts(ds), xin, mk)
+    dec, pre, zq, idx = engines(ds, "tc").forward(torch.from_numpy(xin).cuda(), torch.from_numpy(mk).to(torch.uint8).cuda())
+    assert tuple(dec.shape) == (1, 4, 512, 512) and tuple(idx.shape) == (1, 32, 32)
+    assert rel(pre.permute(0, 3, 1, 2), pre_o) < 1e-3
+    same = (idx.cpu() == idx_o)
+    assert same.float().mean().item() >= 0.995, f"{(~same).sum().item()} of 1024 tokens differ"
+    if same.all():
+        assert rel(dec, dec_o) < 1e-3
