@@ -1,5 +1,5 @@
-// Stage (iii), tensor-core path (sm_100a): conv 3x3 / 1x1 and the attention products as ONE implicit-GEMM
-// kernel on tcgen05.mma with TMA-staged operands and TMEM accumulators.
+// Stage (iii), tensor-core path (sm_100a): conv 3x3 / 1x1 and the attention products as ONE persistent
+// implicit-GEMM kernel on tcgen05.mma with TMA-staged operands and TMEM accumulators.
 //
 //   D[m, n] = alpha * sum_k A(m, k) * B[n, k]  (+ bias_n[n]) (+ bias_m[m]) (+ R[m, n])
 //
@@ -9,16 +9,23 @@
 // hi*hi + hi*lo + lo*hi, into the same fp32 TMEM accumulator (the dropped lo*lo term is <= 2^-16 relative).
 //
 // Operand staging: activations live in HBM as NHWC bf16 planes.  The A tile of an output-pixel block is one TMA
-// box {64 channels, BW, BH, 1} of the 4-D tensor map (C, W, H, B) shifted by the filter tap (kw-1, kh-1); the
-// out-of-bounds zero fill of TMA *is* the conv padding, so there is no im2col buffer and no bounds code.  The box
-// lands in shared memory as 128 rows x 128 B with the 128-byte swizzle, exactly the K-major canonical layout the
-// UMMA shared-memory descriptor expects.  Weights are [N, taps*C] K-major bf16 planes read through a 3-D map.
+// box {BK channels, BW, BH, 1} of the 4-D tensor map (C, W, H, B) shifted by the filter tap (kw-pad, kh-pad); the
+// out-of-bounds zero fill of TMA *is* the conv padding, so there is no im2col buffer and no bounds code; stride 2
+// uses the map's element strides.  The box lands in shared memory as rows of BK*2 bytes with the matching swizzle
+// (128 B for BK = 64, 64 B for BK = 32), exactly the K-major canonical layout of the UMMA shared-memory descriptor.
+// Weights are [N, taps*C] K-major bf16 planes read through a 3-D map.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue
-// (tcgen05.ld 32x32b, bias / residual / alpha, fp32 or split-bf16 stores).  3-stage mbarrier ring.
+// CTA = 6 warps, persistent (one CTA per SM, static round-robin over tiles): warp 0 TMA producer, warp 1 MMA issuer
+// (+ TMEM allocation), warps 2-5 epilogue (tcgen05.ld 32x32b, bias / residual / alpha, fp32 or split-bf16 stores,
+// fused GroupNorm partial statistics).  The fp32 accumulators are double-buffered in TMEM so the epilogue of tile i
+// overlaps the main loop of tile i+1.  Template parameters: BN (columns per tile), BK / STAGES (depth of the
+// mbarrier ring), MT (128-row pixel blocks per tile that share one weight tile: MT = 2 cuts the L2->SMEM bytes per
+// MMA by 27%, the measured limiter of the 128-channel layers).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
+#include "tc_split.cuh"
 
 namespace {
 
@@ -30,6 +37,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -52,6 +62,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 in, fp32 accumulate), single CTA
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -78,12 +89,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major)
-//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B) | [46,48) version = 1 | [61,64) layout = SWIZZLE_128B (2)
+//   [32,46) stride byte offset >> 4 (8 rows of ROW_BYTES) | [46,48) version = 1
+//   [61,64) layout: SWIZZLE_128B = 2 (128-byte rows), SWIZZLE_64B = 4 (64-byte rows)
+template <int ROW_BYTES>
 __device__ __forceinline__ uint64_t make_smem_desc(const void *tile) {
+    static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "K-major rows are one swizzle span");
     const uint64_t addr = (uint64_t)((smem_u32(tile) & 0x3FFFFu) >> 4);
-    return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    return addr | (1ull << 16) | ((uint64_t)((8 * ROW_BYTES) >> 4) << 32) | (1ull << 46) | ((ROW_BYTES == 128 ? 2ull : 4ull) << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
 // K-major A and B (0) @15/@16, N >> 3 @17, M >> 4 @24
@@ -91,25 +105,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-}
-
 // ------------------------------------------------------------------------------------------------ the GEMM kernel
-constexpr int BM = 128, BK = 64, STAGES = 3, TC_THREADS = 192;
-constexpr int A_TILE_BYTES = BM * BK * 2;          // 16 KB
+constexpr int TC_THREADS = 192;
 
 struct TcParams {
-    // tiling of M: m-tile -> (b, ty, tx); rows of the tile are (ly, lx) with lx < BW, ly < BH, BW*BH = 128
+    // tiling of M: m-tile -> (b, ty, tx); rows of the tile are (ly, lx) with lx < BW, ly < BH, BW*BH = 128*MT
     int tiles_x, tiles_y, BW, BH;
     int tiles_m, tiles_n;       // persistent schedule: tile id = m_tile * tiles_n + n_tile (the n-tiles of one pixel block
                                 // run on neighbouring SMs at the same time, so the A box is fetched from HBM once)
     int Ho, Wo;                 // output pixel grid per batch element (plain GEMM: Ho = 1, Wo = M)
     int taps, ks, pad, stride;  // conv: ks*ks taps, left/top pad, stride; plain GEMM: taps = 1, ks = 1, pad = 0, stride = 1
-    int kblocks_per_tap;        // C / 64 (rounded up)
+    int kblocks_per_tap;        // ceil(C / BK)
     int N;                      // total output columns (row stride of D)
     int n_valid;                // columns actually stored (< N only for the zero-padded small-Cout head)
     int out_nchw;               // store D as [b][n][oy][ox] (decoder conv_out) instead of row-major [m][n]
@@ -120,14 +126,9 @@ struct TcParams {
     const float *bias_n, *bias_m, *R;
     float *D;                   // fp32 output (or null)
     __nv_bfloat16 *D_hi, *D_lo; // split-bf16 output (or null)
-    float *stats;               // or null: per-(batch, pixel-block) GroupNorm partial sums [B][tiles_y*tiles_x][32][2]
+    float *stats;               // or null: GroupNorm partial sums per (batch, 128-pixel block) [B][blocks][32][2]
     int cpg;                    // channels per group = N / 32 when stats != null
 };
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // per-warp GroupNorm partial sums of one 32-column chunk: CPG channels per group, rows = lanes
 template <int CPG>
@@ -144,15 +145,26 @@ __device__ __forceinline__ void chunk_group_sums(const float (&o)[32], bool row_
     }
 }
 
-template <int BN>
+template <int BN, int BK, int STAGES, int MT>
+struct TcCfg {
+    static constexpr int ROW_BYTES = BK * 2;
+    static constexpr int A_PLANE = MT * 128 * ROW_BYTES;      // one of (hi, lo)
+    static constexpr int B_PLANE = BN * ROW_BYTES;
+    static constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;
+    static constexpr int TMEM_COLS = (2 * MT * BN < 32) ? 32 : 2 * MT * BN;   // double-buffered accumulators
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
+    static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation is a power of two <= 512 columns");
+    static_assert(SMEM <= 227 * 1024, "stage ring exceeds shared memory");
+};
+
+template <int BN, int BK, int STAGES, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams p) {
-    constexpr int B_TILE_BYTES = BN * BK * 2;
-    constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;        // two accumulator buffers
+    using Cfg = TcCfg<BN, BK, STAGES, MT>;
+    constexpr int ROW_BYTES = Cfg::ROW_BYTES, A_PLANE = Cfg::A_PLANE, B_PLANE = Cfg::B_PLANE, STAGE_BYTES = Cfg::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B needs 1024-B alignment
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // swizzle atoms need 1024-B alignment
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float stat_s[4][BN / 4 * 2];        // [epilogue warp][group in tile][sum, sumsq]  (cpg >= 4)
@@ -166,8 +178,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // one full warp allocates the TMEM columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS) : "memory");
+    if (warp == 1) {   // one full warp allocates the TMEM columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -178,7 +190,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_TILE_BYTES + B_TILE_BYTES);
+            const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_PLANE + B_PLANE);
             int kbg = 0;                                              // k-block counter across tiles (ring position)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n0 = (tile % p.tiles_n) * BN;
@@ -195,10 +207,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                     const int cx = tx * p.BW * p.stride + kw - p.pad, cy = ty * p.BH * p.stride + kh - p.pad;
                     mbar_expect_tx(&full_bar[s], tx_bytes);
                     tma_load_4d(st, &mapA_hi, &full_bar[s], kc * BK, cx, cy, ab);
-                    tma_load_3d(st + 2 * A_TILE_BYTES, &mapB_hi, &full_bar[s], kb * BK, n0, bb);
+                    tma_load_3d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], kb * BK, n0, bb);
                     if (p.nsplit == 3) {
-                        tma_load_4d(st + A_TILE_BYTES, &mapA_lo, &full_bar[s], kc * BK, cx, cy, ab);
-                        tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &mapB_lo, &full_bar[s], kb * BK, n0, bb);
+                        tma_load_4d(st + A_PLANE, &mapA_lo, &full_bar[s], kc * BK, cx, cy, ab);
+                        tma_load_3d(st + 2 * A_PLANE + B_PLANE, &mapB_lo, &full_bar[s], kb * BK, n0, bb);
                     }
                 }
             }
@@ -206,39 +218,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
+            constexpr uint32_t idesc = make_idesc(128, BN);
             int kbg = 0, li = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
                 const int acc = li & 1;
-                mbar_wait(&tmem_empty_bar[acc], ((li >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+                mbar_wait(&tmem_empty_bar[acc], ((li >> 1) & 1) ^ 1);     // epilogue has drained this accumulator set
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
                     const int s = kbg % STAGES, it = kbg / STAGES;
                     mbar_wait(&full_bar[s], it & 1);
                     tc_fence_after();
                     uint8_t *st = smem + (size_t)s * STAGE_BYTES;
-                    const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_TILE_BYTES);
-                    const uint64_t b_hi = make_smem_desc(st + 2 * A_TILE_BYTES), b_lo = make_smem_desc(st + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                    const uint64_t b_hi = make_smem_desc<ROW_BYTES>(st + 2 * A_PLANE), b_lo = make_smem_desc<ROW_BYTES>(st + 2 * A_PLANE + B_PLANE);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {            // UMMA_K = 16 bf16 = 32 B: advance the start address field by 2
-                        const uint64_t off = (uint64_t)(k * 2);
-                        umma_bf16(tmem_d, a_hi + off, b_hi + off, idesc, (kb | k) ? 1u : 0u);
-                        if (p.nsplit == 3) {
-                            umma_bf16(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
-                            umma_bf16(tmem_d, a_lo + off, b_hi + off, idesc, 1u);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t tmem_d = tmem_base + (uint32_t)((acc * MT + mt) * BN);
+                        const uint64_t a_hi = make_smem_desc<ROW_BYTES>(st + mt * 128 * ROW_BYTES);
+                        const uint64_t a_lo = make_smem_desc<ROW_BYTES>(st + A_PLANE + mt * 128 * ROW_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {        // UMMA_K = 16 bf16 = 32 B: advance the start address field by 2
+                            const uint64_t off = (uint64_t)(k * 2);
+                            umma_bf16(tmem_d, a_hi + off, b_hi + off, idesc, (kb | k) ? 1u : 0u);
+                            if (p.nsplit == 3) {
+                                umma_bf16(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
+                                umma_bf16(tmem_d, a_lo + off, b_hi + off, idesc, 1u);
+                            }
                         }
                     }
                     umma_commit(&empty_bar[s]);                     // frees the stage when these MMAs retire
                 }
-                umma_commit(&tmem_full_bar[acc]);                   // accumulator complete
+                umma_commit(&tmem_full_bar[acc]);                   // accumulators complete
             }
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4).. =====
         const int q = warp & 3;
-        const int r = q * 32 + lane;                           // tile row = TMEM lane
-        const int ly = r / p.BW, lx = r - ly * p.BW;
         int li = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
             const int acc = li & 1;
@@ -247,93 +261,99 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             const int m_tile = t % (p.tiles_x * p.tiles_y);
             const int tx = t % p.tiles_x; t /= p.tiles_x;
             const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
-            const int oy = ty * p.BH + ly, ox = tx * p.BW + lx;
-            const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
-            const long long m = (long long)oy * p.Wo + ox;          // row within the batch slice
-            const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
-            const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
             mbar_wait(&tmem_full_bar[acc], (li >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                const int n = n0 + c0;
-                if (n >= p.n_valid) continue;
-                float o[32];
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = mt * 128 + q * 32 + lane;                 // row of the box; TMEM lane = r % 128
+                const int ly = r / p.BW, lx = r - ly * p.BW;
+                const int oy = ty * p.BH + ly, ox = tx * p.BW + lx;
+                const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
+                const long long m = (long long)oy * p.Wo + ox;          // row within the batch slice
+                const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
+                const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * BN + c0), v);
+                    const int n = n0 + c0;
+                    if (n >= p.n_valid) continue;
+                    float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bm;
-                if (p.out_nchw || n + 32 > p.n_valid) {      // ragged / NCHW tail (the 4-channel head): scalar stores, coalesced over ox
-                    if (row_ok) {
+                    for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bm;
+                    if (p.out_nchw || n + 32 > p.n_valid) {      // ragged / NCHW tail (the 4-channel head): scalar stores, coalesced over ox
+                        if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (n + j < p.n_valid) {
-                                float val = o[j] + (p.bias_n ? __ldg(p.bias_n + n + j) : 0.0f);
-                                if (p.out_nchw) p.D[(((long long)b * p.n_valid + n + j) * p.Ho + oy) * p.Wo + ox] = val;
-                                else p.D[row_off + n + j] = val + (p.R ? __ldg(p.R + row_off + n + j) : 0.0f);
+                            for (int j = 0; j < 32; ++j) {
+                                if (n + j < p.n_valid) {
+                                    float val = o[j] + (p.bias_n ? __ldg(p.bias_n + n + j) : 0.0f);
+                                    if (p.out_nchw) p.D[(((long long)b * p.n_valid + n + j) * p.Ho + oy) * p.Wo + ox] = val;
+                                    else p.D[row_off + n + j] = val + (p.R ? __ldg(p.R + row_off + n + j) : 0.0f);
+                                }
                             }
                         }
+                        continue;
                     }
-                    continue;
-                }
-                if (p.bias_n) {
+                    if (p.bias_n) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias_n + n + j));
-                        o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(p.bias_n + n + j));
+                            o[j] += bv.x; o[j + 1] += bv.y; o[j + 2] += bv.z; o[j + 3] += bv.w;
+                        }
+                    }
+                    if (p.R && row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.R + row_off + n + j));
+                            o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+                        }
+                    }
+                    if (p.stats) {                                // GroupNorm statistics of the finished output, per warp
+                        float *dst = &stat_s[q][(c0 / p.cpg) * 2];
+                        if (p.cpg == 4) chunk_group_sums<4>(o, row_ok, lane, dst);
+                        else if (p.cpg == 8) chunk_group_sums<8>(o, row_ok, lane, dst);
+                        else chunk_group_sums<16>(o, row_ok, lane, dst);
+                    }
+                    if (!row_ok) continue;
+                    if (p.D) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(p.D + row_off + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                    }
+                    if (p.D_hi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) split2(o[j], o[j + 1], hi[j / 2], lo[j / 2]);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            *reinterpret_cast<uint4 *>(p.D_hi + row_off + n + 2 * j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+                            *reinterpret_cast<uint4 *>(p.D_lo + row_off + n + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                        }
                     }
                 }
-                if (p.R && row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.R + row_off + n + j));
-                        o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+                if (p.stats) {
+                    epilogue_bar_sync();
+                    const int e = threadIdx.x - 64;                     // 0..127
+                    const int nvals = (BN / p.cpg) * 2;
+                    if (e < nvals) {
+                        const float v = (stat_s[0][e] + stat_s[1][e]) + (stat_s[2][e] + stat_s[3][e]);
+                        const int g = n0 / p.cpg + (e >> 1);
+                        const long long slot = ((long long)b * (p.tiles_x * p.tiles_y) + m_tile) * MT + mt;
+                        p.stats[(slot * 32 + g) * 2 + (e & 1)] = v;
                     }
-                }
-                if (p.stats) {                                // GroupNorm statistics of the finished output, per warp
-                    float *dst = &stat_s[q][(c0 / p.cpg) * 2];
-                    if (p.cpg == 4) chunk_group_sums<4>(o, row_ok, lane, dst);
-                    else if (p.cpg == 8) chunk_group_sums<8>(o, row_ok, lane, dst);
-                    else chunk_group_sums<16>(o, row_ok, lane, dst);
-                }
-                if (!row_ok) continue;
-                if (p.D) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4 *>(p.D + row_off + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                }
-                if (p.D_hi) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) split2(o[j], o[j + 1], hi[j / 2], lo[j / 2]);
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        *reinterpret_cast<uint4 *>(p.D_hi + row_off + n + 2 * j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
-                        *reinterpret_cast<uint4 *>(p.D_lo + row_off + n + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
-                    }
+                    epilogue_bar_sync();
                 }
             }
-            // this accumulator buffer may be overwritten by the MMA warp as soon as all four warps have read it
+            // this accumulator set may be overwritten by the MMA warp as soon as all four warps have read it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            if (p.stats) {
-                epilogue_bar_sync();
-                const int e = threadIdx.x - 64;                     // 0..127
-                const int nvals = (BN / p.cpg) * 2;
-                if (e < nvals) {
-                    const float v = (stat_s[0][e] + stat_s[1][e]) + (stat_s[2][e] + stat_s[3][e]);
-                    const int g = n0 / p.cpg + (e >> 1);
-                    p.stats[(((long long)b * (p.tiles_x * p.tiles_y) + m_tile) * 32 + g) * 2 + (e & 1)] = v;
-                }
-                epilogue_bar_sync();
-            }
         }
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -353,7 +373,7 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// bf16 tensor [d3][d2][d1][d0] (d0 innermost, contiguous), box {b0, b1, b2, 1}, 128-byte swizzle, zero OOB fill
+// bf16 tensor [d3][d2][d1][d0] (d0 innermost, contiguous), box {b0, b1, b2, 1}, swizzle span = box[0] * 2 bytes, zero OOB fill
 int make_map(CUtensorMap *m, const void *base, int rank, const long long *dims, const int *box, const int *estride = nullptr) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { sgam_set_error("cuTensorMapEncodeTiled is unavailable"); return SGAM_ERR_CUDA; }
@@ -365,9 +385,9 @@ int make_map(CUtensorMap *m, const void *base, int rank, const long long *dims, 
         stride *= (unsigned long long)dims[i];
         if (i < rank - 1) gs[i] = stride;
     }
+    const CUtensorMapSwizzle sw = (box[0] == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bd, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { sgam_set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %lld %lld %lld)", (int)r, rank, dims[0], dims[1], rank > 2 ? dims[2] : 0); return SGAM_ERR_CUDA; }
     return SGAM_OK;
 }
@@ -383,251 +403,80 @@ int sm_count_cached() {
     return n;
 }
 
-template <int BN>
-int launch_tc(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, TcParams p,
-              int tiles_m, int N, cudaStream_t s) {
-    constexpr size_t smem = (size_t)STAGES * (2 * A_TILE_BYTES + 2 * BN * BK * 2) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+// Kernel variant: SGAM_TC_VARIANT = 0 (BK 64, 3 stages), 1 (BK 32, deeper ring), 2 (BK 32, two pixel blocks per weight tile)
+int tc_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SGAM_TC_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
     }
-    p.tiles_m = tiles_m;
-    p.tiles_n = cdiv(N, BN);
-    const int total = p.tiles_m * p.tiles_n;
-    const int grid = total < sm_count_cached() ? total : sm_count_cached();      // persistent: one CTA per SM
-    tc_gemm_kernel<BN><<<grid, TC_THREADS, smem, s>>>(a_hi, a_lo, b_hi, b_lo, p);
-    SGAM_LAUNCH_OK();
-    return SGAM_OK;
+    return v;
 }
 
-// ------------------------------------------------------------------------------------------------ producers of split bf16
-// x fp32 [B, H, W, C] -> hi / lo bf16 [B, H<<up, W<<up, C] (nearest x2 up-sampling fused when up = 1)
-__global__ void __launch_bounds__(256)
-split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
-                  long long total_q, int H, int W, int CQ, int up) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_q; e += (long long)gridDim.x * blockDim.x) {
-        long long src = e;
-        if (up) {
-            const int cq = (int)(e % CQ);
-            long long pix = e / CQ;
-            const int Wo = W * 2, Ho = H * 2;
-            const int ox = (int)(pix % Wo); pix /= Wo;
-            const int oy = (int)(pix % Ho); const long long b = pix / Ho;
-            src = (((b * H + (oy >> 1)) * W + (ox >> 1)) * CQ) + cq;
-        }
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + src);
-        uint32_t h[2], l[2];
-        split2(v.x, v.y, h[0], l[0]);
-        split2(v.z, v.w, h[1], l[1]);
-        reinterpret_cast<uint2 *>(hi)[e] = make_uint2(h[0], h[1]);
-        reinterpret_cast<uint2 *>(lo)[e] = make_uint2(l[0], l[1]);
-    }
-}
+struct TilePlan {
+    int BN, BK, MT, BW, BH;     // BW * BH = 128 * MT output pixels per tile
+};
 
-// GroupNorm apply (+ swish) with split-bf16 output; statistics come from gn_stats (net_simt.cu) partials
-__global__ void __launch_bounds__(256)
-gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ meanrstd,
-                      const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ hi,
-                      __nv_bfloat16 *__restrict__ lo, long long HW, int C, int S, int swish) {
-    __shared__ float mean_s[32], rstd_s[32];
-    const int b = blockIdx.y, tid = threadIdx.x;
-    if (meanrstd) {                     // statistics already finalised (fused into the producing conv's epilogue)
-        if (tid < 32) { mean_s[tid] = meanrstd[(b * 32 + tid) * 2]; rstd_s[tid] = meanrstd[(b * 32 + tid) * 2 + 1]; }
-    } else if (tid < 32) {
-        double a = 0.0, q = 0.0;
-        for (int s = 0; s < S; ++s) {
-            const double *src = partial + (((size_t)b * S + s) * 32 + tid) * 2;
-            a += src[0]; q += src[1];
-        }
-        const double n = (double)HW * (C / 32), mean = a / n;
-        double var = q / n - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        mean_s[tid] = (float)mean;
-        rstd_s[tid] = (float)(1.0 / sqrt(var + 1e-6));
-    }
-    __syncthreads();
-    const int CQ = C / 4, cpg = C / 32;
-    const long long total = HW * CQ;
-    const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)b * HW * C);
-    uint2 *dh = reinterpret_cast<uint2 *>(hi + (size_t)b * HW * C), *dl = reinterpret_cast<uint2 *>(lo + (size_t)b * HW * C);
-    for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(e % CQ), c = cq * 4, g = c / cpg;
-        const float mu = mean_s[g], rs = rstd_s[g];
-        const float4 v = __ldg(src + e), ga = __ldg(reinterpret_cast<const float4 *>(gamma + c)),
-                     be = __ldg(reinterpret_cast<const float4 *>(beta + c));
-        float o[4] = {(v.x - mu) * rs * ga.x + be.x, (v.y - mu) * rs * ga.y + be.y,
-                      (v.z - mu) * rs * ga.z + be.z, (v.w - mu) * rs * ga.w + be.w};
-        if (swish) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.0f + expf(-o[k]));
-        }
-        uint32_t h[2], l[2];
-        split2(o[0], o[1], h[0], l[0]);
-        split2(o[2], o[3], h[1], l[1]);
-        dh[e] = make_uint2(h[0], h[1]);
-        dl[e] = make_uint2(l[0], l[1]);
-    }
-}
-
-// row softmax of fp32 scores -> split-bf16 probabilities (model.py:181); cols % 2 == 0.
-// VPT > 0: the row (cols <= 256*2*VPT) is read ONCE into registers (8 B in, 8 B out per pair); VPT = 0: three-pass fallback.
-template <int VPT>
-__global__ void __launch_bounds__(256)
-softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cols) {
-    __shared__ float sh[8];
-    const float *row = x + (size_t)blockIdx.x * cols;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = cols / 2;
-    uint32_t *dh = reinterpret_cast<uint32_t *>(hi + (size_t)blockIdx.x * cols), *dl = reinterpret_cast<uint32_t *>(lo + (size_t)blockIdx.x * cols);
-    float2 v[VPT > 0 ? VPT : 1];
-    float mx = -INFINITY;
-    if (VPT > 0) {
-#pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-            const int c = threadIdx.x + i * 256;
-            v[i] = (c < half) ? __ldg(reinterpret_cast<const float2 *>(row) + c) : make_float2(-INFINITY, -INFINITY);
-            mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
-        }
-    } else {
-        for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, row[c]);
-    }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) sh[warp] = mx;
-    __syncthreads();
-    mx = sh[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
-    __syncthreads();
-    float sum = 0.f;
-    if (VPT > 0) {
-#pragma unroll
-        for (int i = 0; i < VPT; ++i) { v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx); sum += v[i].x + v[i].y; }
-    } else {
-        for (int c = threadIdx.x; c < cols; c += 256) sum += expf(row[c] - mx);
-    }
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) sh[warp] = sum;
-    __syncthreads();
-    sum = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) sum += sh[w];
-    const float inv = 1.0f / sum;
-    if (VPT > 0) {
-#pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-            const int c = threadIdx.x + i * 256;
-            if (c < half) { uint32_t h, l; split2(v[i].x * inv, v[i].y * inv, h, l); dh[c] = h; dl[c] = l; }
-        }
-    } else {
-        for (int c = threadIdx.x; c < half; c += 256) {
-            const float2 t = *reinterpret_cast<const float2 *>(row + 2 * c);
-            uint32_t h, l;
-            split2(expf(t.x - mx) * inv, expf(t.y - mx) * inv, h, l);
-            dh[c] = h; dl[c] = l;
-        }
-    }
-}
-
-// reduce the per-pixel-block partial sums written by tc_gemm_kernel's epilogue: [B][tiles][32][2] fp32 -> mean, rstd
-__global__ void __launch_bounds__(256)
-gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrstd, int tiles, double count) {
-    __shared__ double red[8][32][2];
-    const int b = blockIdx.x, g = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double a = 0.0, q = 0.0;
-    for (int t = w; t < tiles; t += 8) {
-        const float2 v = *reinterpret_cast<const float2 *>(partial + (((size_t)b * tiles + t) * 32 + g) * 2);
-        a += (double)v.x; q += (double)v.y;
-    }
-    red[w][g][0] = a; red[w][g][1] = q;
-    __syncthreads();
-    if (w == 0) {
-        for (int k = 1; k < 8; ++k) { a += red[k][g][0]; q += red[k][g][1]; }
-        const double mean = a / count;
-        double var = q / count - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        meanrstd[(b * 32 + g) * 2] = (float)mean;
-        meanrstd[(b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-6));
-    }
-}
-
-}  // namespace
-
-// gn_stats launcher lives in net_simt.cu
-int sgam_gn_stats_launch(const float *x, double *partial, int B, long long HW, int C, cudaStream_t s);
-
-extern "C" int sgam_split_bf16(const float *x, void *hi, void *lo, int B, int H, int W, int C, int upsample, void *stream) {
-    SGAM_REQUIRE(x && hi && lo && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "split_bf16: bad arguments");
-    const long long total_q = (long long)B * (H << upsample) * (W << upsample) * (C / 4);
-    const unsigned blocks = (unsigned)min((long long)148 * 16, (total_q + 255) / 256);
-    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, total_q, H, W, C / 4, upsample);
-    SGAM_LAUNCH_OK();
-    return SGAM_OK;
-}
-
-extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const float *beta, void *hi, void *lo, double *partial,
-                                    int B, long long HW, int C, int swish, void *stream) {
-    SGAM_REQUIRE(x && gamma && beta && hi && lo && partial, "groupnorm_split: null pointer");
-    SGAM_REQUIRE(B > 0 && HW > 0 && C % 128 == 0 && C <= 1024, "groupnorm_split: C=%d must be a multiple of 128 (<= 1024)", C);
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = sgam_gn_stats_launch(x, partial, B, HW, C, s);
-    if (rc) return rc;
-    const long long total = HW * (C / 4);
-    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
-    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
-                                                          sgam_gn_splits(HW), swish);
-    SGAM_LAUNCH_OK();
-    return SGAM_OK;
-}
-
-extern "C" long long sgam_tc_gn_partial_floats(int B, int Ho, int Wo) {
-    const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
-    const long long tiles = (long long)cdiv(Wo, BW) * cdiv(Ho, BH);
-    return (long long)B * tiles * 64 + (long long)B * 64;           // partial sums, then [B][32][mean, rstd]
-}
-
-extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
-                                          float *gn_partial, int B, int Ho, int Wo, int C, int swish, void *stream) {
-    SGAM_REQUIRE(x && gamma && beta && hi && lo && gn_partial, "groupnorm_split_fused: null pointer");
-    SGAM_REQUIRE(B > 0 && Ho > 0 && Wo > 0 && C % 128 == 0 && C <= 512, "groupnorm_split_fused: C=%d must be 128, 256, 384 or 512", C);
-    cudaStream_t s = (cudaStream_t)stream;
-    const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
-    const int tiles = cdiv(Wo, BW) * cdiv(Ho, BH);
-    const long long HW = (long long)Ho * Wo;
-    float *meanrstd = gn_partial + (long long)B * tiles * 64;
-    gn_finalize_kernel<<<B, 256, 0, s>>>(gn_partial, meanrstd, tiles, (double)HW * (C / 32));
-    SGAM_LAUNCH_OK();
-    const long long total = HW * (C / 4);
-    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
-    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
-    SGAM_LAUNCH_OK();
-    return SGAM_OK;
-}
-
-extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long rows, int cols, void *stream) {
-    SGAM_REQUIRE(x && hi && lo && rows > 0 && cols > 0 && cols % 2 == 0, "softmax_split: bad arguments");
-    cudaStream_t s = (cudaStream_t)stream;
-    __nv_bfloat16 *h = (__nv_bfloat16 *)hi, *l = (__nv_bfloat16 *)lo;
-    if (cols <= 512) softmax_split_kernel<1><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else if (cols <= 2048) softmax_split_kernel<4><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else if (cols <= 4096) softmax_split_kernel<8><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else if (cols <= 16384) softmax_split_kernel<32><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else softmax_split_kernel<0><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    SGAM_LAUNCH_OK();
-    return SGAM_OK;
-}
-
-static int pick_bw(int W) { return W >= 128 ? 128 : W; }
-
-// Column-tile width: 128 unless the grid would leave most of the 148 SMs idle, in which case 64-wide tiles double
-// the tile count (tcgen05 runs N=64 at the same MAC rate).  Cost model: waves * (BN + fixed per-tile overhead).
-static int pick_bn(int tiles_m, int N) {
+// Column-tile width: 128 unless the grid would leave most of the SMs idle, in which case 64-wide tiles double the
+// tile count (tcgen05 runs N = 64 at the same MAC rate).  Cost model: waves * (BN + fixed per-tile overhead).
+int pick_bn(long long tiles_m, int N) {
     if (N % 64) return 32;
     if (N % 128) return 64;
     const int sms = sm_count_cached();
-    const long long t128 = (long long)tiles_m * (N / 128), t64 = (long long)tiles_m * (N / 64);
+    const long long t128 = tiles_m * (N / 128), t64 = tiles_m * (N / 64);
     const long long c128 = ((t128 + sms - 1) / sms) * (128 + 32), c64 = ((t64 + sms - 1) / sms) * (64 + 32);
     return c64 < c128 ? 64 : 128;
 }
+
+TilePlan plan_tiles(int B, int Ho, int Wo, int N) {
+    TilePlan t;
+    const int BW1 = Wo >= 128 ? 128 : Wo, BH1 = 128 / BW1;
+    const long long tiles1 = (long long)cdiv(Wo, BW1) * cdiv(Ho, BH1) * B;
+    t.BN = pick_bn(tiles1, N);
+    t.BK = 64; t.MT = 1; t.BW = BW1; t.BH = BH1;
+    const int v = tc_variant();
+    if (v >= 1 && t.BN >= 64) t.BK = 32;
+    if (v == 2 && t.BN >= 64) {
+        // two 128-pixel blocks per tile when the grid stays full and the blocks tile the image exactly
+        const int BW2 = Wo >= 256 ? 256 : Wo, BH2 = 256 / BW2;
+        const bool exact = (Wo >= 256) ? (Wo % 256 == 0) : (256 % Wo == 0 && Ho % BH2 == 0);
+        if (exact && tiles1 * (N / t.BN) >= 4LL * sm_count_cached()) { t.MT = 2; t.BW = BW2; t.BH = BH2; }
+    }
+    return t;
+}
+
+template <int BN, int BK, int STAGES, int MT>
+int launch_cfg(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, const TcParams &p, cudaStream_t s) {
+    using Cfg = TcCfg<BN, BK, STAGES, MT>;
+    static bool configured = false;
+    if (!configured) {
+        SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int total = p.tiles_m * p.tiles_n;
+    const int grid = total < sm_count_cached() ? total : sm_count_cached();      // persistent: one CTA per SM
+    tc_gemm_kernel<BN, BK, STAGES, MT><<<grid, TC_THREADS, Cfg::SMEM, s>>>(a_hi, a_lo, b_hi, b_lo, p);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+int launch_tc(const TilePlan &t, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo,
+              TcParams p, int tiles_m, int Npad, cudaStream_t s) {
+    p.tiles_m = tiles_m;
+    p.tiles_n = cdiv(Npad, t.BN);
+    if (t.BN == 128 && t.BK == 64) return launch_cfg<128, 64, 3, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
+    if (t.BN == 64 && t.BK == 64) return launch_cfg<64, 64, 4, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
+    if (t.BN == 32) return launch_cfg<32, 64, 4, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
+    if (t.BN == 128 && t.MT == 1) return launch_cfg<128, 32, 6, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
+    if (t.BN == 64 && t.MT == 1) return launch_cfg<64, 32, 8, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
+    if (t.BN == 128 && t.MT == 2) return launch_cfg<128, 32, 4, 2>(a_hi, a_lo, b_hi, b_lo, p, s);
+    if (t.BN == 64 && t.MT == 2) return launch_cfg<64, 32, 5, 2>(a_hi, a_lo, b_hi, b_lo, p, s);
+    sgam_set_error("tc_gemm: no kernel for BN=%d BK=%d MT=%d", t.BN, t.BK, t.MT);
+    return SGAM_ERR_UNSUPPORTED;
+}
+
+}  // namespace
 
 extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int stride) {
     // H, W: OUTPUT grid.  stride 2 is the Downsample (pad right/bottom, model.py:68-72).
@@ -648,32 +497,27 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
     SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "conv2d_tc: nsplit must be 1 or 3");
     const int Npad = (Cout + 31) / 32 * 32;             // weight planes carry Npad rows (zero rows beyond Cout)
     SGAM_REQUIRE(!(out_nchw || Npad != Cout) || (y && !y_hi && !residual), "conv2d_tc: NCHW / ragged-Cout output is fp32 without residual");
-    const int BW = pick_bw(Wo), BH = 128 / BW;
+    TilePlan t = plan_tiles(B, Ho, Wo, Npad);
+    if (stride == 2 && t.MT == 2) { t.MT = 1; t.BW = Wo >= 128 ? 128 : Wo; t.BH = 128 / t.BW; }   // TMA box extent <= 256 elements
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     const long long adims[4] = {Cin, W, H, B};
-    const int abox[4] = {BK, BW * stride, BH * stride, 1};
+    const int abox[4] = {t.BK, t.BW * stride, t.BH * stride, 1};
     const int astr[4] = {1, stride, stride, 1};
     const int taps = ksize * ksize;
     const long long bdims[3] = {(long long)taps * Cin, Npad, 1};
-    const int BN = pick_bn(cdiv(Wo, BW) * cdiv(Ho, BH) * B, Npad);
-    const int bbox[3] = {BK, BN, 1};
+    const int bbox[3] = {t.BK, t.BN, 1};
     int rc;
     if ((rc = make_map(&a_hi, x_hi, 4, adims, abox, astr)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox, astr)) ||
         (rc = make_map(&b_hi, w_hi, 3, bdims, bbox)) || (rc = make_map(&b_lo, w_lo, 3, bdims, bbox)))
         return rc;
     TcParams p{};
-    p.tiles_x = cdiv(Wo, BW); p.tiles_y = cdiv(Ho, BH); p.BW = BW; p.BH = BH; p.Ho = Ho; p.Wo = Wo;
-    p.taps = taps; p.ks = ksize; p.pad = (stride == 1) ? ksize / 2 : 0; p.stride = stride; p.kblocks_per_tap = Cin / BK;
-    p.N = out_nchw ? Cout : Npad; p.n_valid = Cout; p.out_nchw = out_nchw; p.nsplit = nsplit;
-    if (!out_nchw && Npad != Cout) p.N = Cout;
+    p.tiles_x = cdiv(Wo, t.BW); p.tiles_y = cdiv(Ho, t.BH); p.BW = t.BW; p.BH = t.BH; p.Ho = Ho; p.Wo = Wo;
+    p.taps = taps; p.ks = ksize; p.pad = (stride == 1) ? ksize / 2 : 0; p.stride = stride; p.kblocks_per_tap = Cin / t.BK;
+    p.N = Cout; p.n_valid = Cout; p.out_nchw = out_nchw; p.nsplit = nsplit;
     p.a_batched = 1; p.b_batched = 0; p.d_batch_stride = (long long)Ho * Wo * Cout; p.alpha = 1.0f;
     p.bias_n = bias; p.bias_m = nullptr; p.R = residual; p.D = y; p.D_hi = (__nv_bfloat16 *)y_hi; p.D_lo = (__nv_bfloat16 *)y_lo;
     p.stats = gn_partial; p.cpg = Cout / 32;
-    const int tiles_m = p.tiles_x * p.tiles_y * B;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (BN == 128) return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, s);
-    if (BN == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, s);
-    return launch_tc<32>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, s);
+    return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, p.tiles_x * p.tiles_y * B, Npad, (cudaStream_t)stream);
 }
 
 extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const void *b_hi_p, const void *b_lo_p, const float *bias_m,
@@ -682,25 +526,23 @@ extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const voi
     SGAM_REQUIRE(a_hi_p && a_lo_p && b_hi_p && b_lo_p && (C || (c_hi && c_lo)), "gemm_nt_tc: null pointer");
     SGAM_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 32 == 0, "gemm_nt_tc: needs K %% 8 == 0 and N %% 32 == 0 (M=%d N=%d K=%d)", M, N, K);
     SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_nt_tc: nsplit must be 1 or 3");
+    TilePlan t = plan_tiles(batch, 1, (M + 127) / 128 * 128, N);       // rows of the plain GEMM tile like one image row
+    if (t.MT == 2 && M % 256) t.MT = 1;
+    t.BH = 1; t.BW = 128 * t.MT;
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     const long long adims[4] = {K, M, 1, a_batched ? batch : 1};
-    const int abox[4] = {BK, 128, 1, 1};
+    const int abox[4] = {t.BK, t.BW, 1, 1};
     const long long bdims[3] = {K, N, b_batched ? batch : 1};
-    const int BN = pick_bn(cdiv(M, 128) * batch, N);
-    const int bbox[3] = {BK, BN, 1};
+    const int bbox[3] = {t.BK, t.BN, 1};
     int rc;
     if ((rc = make_map(&a_hi, a_hi_p, 4, adims, abox)) || (rc = make_map(&a_lo, a_lo_p, 4, adims, abox)) ||
         (rc = make_map(&b_hi, b_hi_p, 3, bdims, bbox)) || (rc = make_map(&b_lo, b_lo_p, 3, bdims, bbox)))
         return rc;
     TcParams p{};
-    p.tiles_x = cdiv(M, 128); p.tiles_y = 1; p.BW = 128; p.BH = 1; p.Ho = 1; p.Wo = M;
-    p.taps = 1; p.ks = 1; p.pad = 0; p.stride = 1; p.kblocks_per_tap = cdiv(K, BK); p.N = N; p.n_valid = N; p.out_nchw = 0; p.nsplit = nsplit;
+    p.tiles_x = cdiv(M, t.BW); p.tiles_y = 1; p.BW = t.BW; p.BH = 1; p.Ho = 1; p.Wo = M;
+    p.taps = 1; p.ks = 1; p.pad = 0; p.stride = 1; p.kblocks_per_tap = cdiv(K, t.BK); p.N = N; p.n_valid = N; p.out_nchw = 0; p.nsplit = nsplit;
     p.a_batched = a_batched; p.b_batched = b_batched; p.d_batch_stride = (long long)M * N; p.alpha = alpha;
     p.bias_n = nullptr; p.bias_m = bias_m; p.R = nullptr; p.D = C; p.D_hi = (__nv_bfloat16 *)c_hi; p.D_lo = (__nv_bfloat16 *)c_lo;
     p.stats = nullptr; p.cpg = 0;
-    const int tiles_m = p.tiles_x * batch;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (BN == 128) return launch_tc<128>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, N, s);
-    if (BN == 64) return launch_tc<64>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, N, s);
-    return launch_tc<32>(a_hi, a_lo, b_hi, b_lo, p, tiles_m, N, s);
+    return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, p.tiles_x * batch, N, (cudaStream_t)stream);
 }

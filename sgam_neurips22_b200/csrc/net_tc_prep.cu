@@ -1,0 +1,224 @@
+// Producers of the tensor-core path's split-bf16 operands (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)):
+// fp32 -> split (+ fused nearest x2 up-sampling), GroupNorm apply (+ swish) -> split, row softmax -> split, and the
+// finaliser of the GroupNorm statistics that tc_gemm_kernel's epilogue emits.  All HBM-bound, 8 B per element.
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_split.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ producers of split bf16
+// x fp32 [B, H, W, C] -> hi / lo bf16 [B, H<<up, W<<up, C] (nearest x2 up-sampling fused when up = 1)
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+                  long long total_q, int H, int W, int CQ, int up) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_q; e += (long long)gridDim.x * blockDim.x) {
+        long long src = e;
+        if (up) {
+            const int cq = (int)(e % CQ);
+            long long pix = e / CQ;
+            const int Wo = W * 2, Ho = H * 2;
+            const int ox = (int)(pix % Wo); pix /= Wo;
+            const int oy = (int)(pix % Ho); const long long b = pix / Ho;
+            src = (((b * H + (oy >> 1)) * W + (ox >> 1)) * CQ) + cq;
+        }
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + src);
+        uint32_t h[2], l[2];
+        split2(v.x, v.y, h[0], l[0]);
+        split2(v.z, v.w, h[1], l[1]);
+        reinterpret_cast<uint2 *>(hi)[e] = make_uint2(h[0], h[1]);
+        reinterpret_cast<uint2 *>(lo)[e] = make_uint2(l[0], l[1]);
+    }
+}
+
+// GroupNorm apply (+ swish) with split-bf16 output; statistics come from gn_stats (net_simt.cu) partials
+__global__ void __launch_bounds__(256)
+gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ meanrstd,
+                      const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ hi,
+                      __nv_bfloat16 *__restrict__ lo, long long HW, int C, int S, int swish) {
+    __shared__ float mean_s[32], rstd_s[32];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (meanrstd) {                     // statistics already finalised (fused into the producing conv's epilogue)
+        if (tid < 32) { mean_s[tid] = meanrstd[(b * 32 + tid) * 2]; rstd_s[tid] = meanrstd[(b * 32 + tid) * 2 + 1]; }
+    } else if (tid < 32) {
+        double a = 0.0, q = 0.0;
+        for (int s = 0; s < S; ++s) {
+            const double *src = partial + (((size_t)b * S + s) * 32 + tid) * 2;
+            a += src[0]; q += src[1];
+        }
+        const double n = (double)HW * (C / 32), mean = a / n;
+        double var = q / n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        mean_s[tid] = (float)mean;
+        rstd_s[tid] = (float)(1.0 / sqrt(var + 1e-6));
+    }
+    __syncthreads();
+    const int CQ = C / 4, cpg = C / 32;
+    const long long total = HW * CQ;
+    const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)b * HW * C);
+    uint2 *dh = reinterpret_cast<uint2 *>(hi + (size_t)b * HW * C), *dl = reinterpret_cast<uint2 *>(lo + (size_t)b * HW * C);
+    for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(e % CQ), c = cq * 4, g = c / cpg;
+        const float mu = mean_s[g], rs = rstd_s[g];
+        const float4 v = __ldg(src + e), ga = __ldg(reinterpret_cast<const float4 *>(gamma + c)),
+                     be = __ldg(reinterpret_cast<const float4 *>(beta + c));
+        float o[4] = {(v.x - mu) * rs * ga.x + be.x, (v.y - mu) * rs * ga.y + be.y,
+                      (v.z - mu) * rs * ga.z + be.z, (v.w - mu) * rs * ga.w + be.w};
+        if (swish) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.0f + expf(-o[k]));
+        }
+        uint32_t h[2], l[2];
+        split2(o[0], o[1], h[0], l[0]);
+        split2(o[2], o[3], h[1], l[1]);
+        dh[e] = make_uint2(h[0], h[1]);
+        dl[e] = make_uint2(l[0], l[1]);
+    }
+}
+
+// row softmax of fp32 scores -> split-bf16 probabilities (model.py:181); cols % 2 == 0.
+// VPT > 0: the row (cols <= 256*2*VPT) is read ONCE into registers (8 B in, 8 B out per pair); VPT = 0: three-pass fallback.
+template <int VPT>
+__global__ void __launch_bounds__(256)
+softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cols) {
+    __shared__ float sh[8];
+    const float *row = x + (size_t)blockIdx.x * cols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = cols / 2;
+    uint32_t *dh = reinterpret_cast<uint32_t *>(hi + (size_t)blockIdx.x * cols), *dl = reinterpret_cast<uint32_t *>(lo + (size_t)blockIdx.x * cols);
+    float2 v[VPT > 0 ? VPT : 1];
+    float mx = -INFINITY;
+    if (VPT > 0) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int c = threadIdx.x + i * 256;
+            v[i] = (c < half) ? __ldg(reinterpret_cast<const float2 *>(row) + c) : make_float2(-INFINITY, -INFINITY);
+            mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
+        }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, row[c]);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sh[warp] = mx;
+    __syncthreads();
+    mx = sh[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sh[w]);
+    __syncthreads();
+    float sum = 0.f;
+    if (VPT > 0) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) { v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx); sum += v[i].x + v[i].y; }
+    } else {
+        for (int c = threadIdx.x; c < cols; c += 256) sum += expf(row[c] - mx);
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) sh[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += sh[w];
+    const float inv = 1.0f / sum;
+    if (VPT > 0) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int c = threadIdx.x + i * 256;
+            if (c < half) { uint32_t h, l; split2(v[i].x * inv, v[i].y * inv, h, l); dh[c] = h; dl[c] = l; }
+        }
+    } else {
+        for (int c = threadIdx.x; c < half; c += 256) {
+            const float2 t = *reinterpret_cast<const float2 *>(row + 2 * c);
+            uint32_t h, l;
+            split2(expf(t.x - mx) * inv, expf(t.y - mx) * inv, h, l);
+            dh[c] = h; dl[c] = l;
+        }
+    }
+}
+
+// reduce the per-pixel-block partial sums written by tc_gemm_kernel's epilogue: [B][tiles][32][2] fp32 -> mean, rstd
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrstd, int tiles, double count) {
+    __shared__ double red[8][32][2];
+    const int b = blockIdx.x, g = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double a = 0.0, q = 0.0;
+    for (int t = w; t < tiles; t += 8) {
+        const float2 v = *reinterpret_cast<const float2 *>(partial + (((size_t)b * tiles + t) * 32 + g) * 2);
+        a += (double)v.x; q += (double)v.y;
+    }
+    red[w][g][0] = a; red[w][g][1] = q;
+    __syncthreads();
+    if (w == 0) {
+        for (int k = 1; k < 8; ++k) { a += red[k][g][0]; q += red[k][g][1]; }
+        const double mean = a / count;
+        double var = q / count - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        meanrstd[(b * 32 + g) * 2] = (float)mean;
+        meanrstd[(b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-6));
+    }
+}
+
+}  // namespace
+
+// gn_stats launcher lives in net_simt.cu
+int sgam_gn_stats_launch(const float *x, double *partial, int B, long long HW, int C, cudaStream_t s);
+
+extern "C" int sgam_split_bf16(const float *x, void *hi, void *lo, int B, int H, int W, int C, int upsample, void *stream) {
+    SGAM_REQUIRE(x && hi && lo && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "split_bf16: bad arguments");
+    const long long total_q = (long long)B * (H << upsample) * (W << upsample) * (C / 4);
+    const unsigned blocks = (unsigned)min((long long)148 * 16, (total_q + 255) / 256);
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, total_q, H, W, C / 4, upsample);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const float *beta, void *hi, void *lo, double *partial,
+                                    int B, long long HW, int C, int swish, void *stream) {
+    SGAM_REQUIRE(x && gamma && beta && hi && lo && partial, "groupnorm_split: null pointer");
+    SGAM_REQUIRE(B > 0 && HW > 0 && C % 128 == 0 && C <= 1024, "groupnorm_split: C=%d must be a multiple of 128 (<= 1024)", C);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = sgam_gn_stats_launch(x, partial, B, HW, C, s);
+    if (rc) return rc;
+    const long long total = HW * (C / 4);
+    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
+    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
+                                                          sgam_gn_splits(HW), swish);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+extern "C" long long sgam_tc_gn_partial_floats(int B, int Ho, int Wo) {
+    const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
+    const long long tiles = (long long)cdiv(Wo, BW) * cdiv(Ho, BH);
+    return (long long)B * tiles * 64 + (long long)B * 64;           // partial sums, then [B][32][mean, rstd]
+}
+
+extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
+                                          float *gn_partial, int B, int Ho, int Wo, int C, int swish, void *stream) {
+    SGAM_REQUIRE(x && gamma && beta && hi && lo && gn_partial, "groupnorm_split_fused: null pointer");
+    SGAM_REQUIRE(B > 0 && Ho > 0 && Wo > 0 && C % 128 == 0 && C <= 512, "groupnorm_split_fused: C=%d must be 128, 256, 384 or 512", C);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
+    const int tiles = cdiv(Wo, BW) * cdiv(Ho, BH);
+    const long long HW = (long long)Ho * Wo;
+    float *meanrstd = gn_partial + (long long)B * tiles * 64;
+    gn_finalize_kernel<<<B, 256, 0, s>>>(gn_partial, meanrstd, tiles, (double)HW * (C / 32));
+    SGAM_LAUNCH_OK();
+    const long long total = HW * (C / 4);
+    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
+    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
+extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long rows, int cols, void *stream) {
+    SGAM_REQUIRE(x && hi && lo && rows > 0 && cols > 0 && cols % 2 == 0, "softmax_split: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    __nv_bfloat16 *h = (__nv_bfloat16 *)hi, *l = (__nv_bfloat16 *)lo;
+    if (cols <= 512) softmax_split_kernel<1><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else if (cols <= 2048) softmax_split_kernel<4><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else if (cols <= 4096) softmax_split_kernel<8><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else if (cols <= 16384) softmax_split_kernel<32><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else softmax_split_kernel<0><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+

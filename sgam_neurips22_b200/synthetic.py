@@ -72,16 +72,22 @@ def scene_step_batch(dataset, res=256, batch=1, seed=0, num_src=None):
 
 
 def randomize_weights(model, seed=0):
-    """Random-init weights for measurements (no checkpoint ships with the reference): default conv init,
-    non-trivial GroupNorm affine, N(0,1) codebook (the default U(+-1/n_e) codebook makes the
-    arg-min ill-conditioned)."""
+    """Seeded random-init weights for measurements (no checkpoint ships with the reference): conv weights / biases
+    U(+-1/sqrt(fan_in)) like torch's default, non-trivial GroupNorm affine, N(0,1) codebook (the
+    default U(+-1/n_e) codebook makes the arg-min ill-conditioned).  Every tensor comes from the one generator, so
+    all ranks / processes / both bench arms see identical weights."""
     import torch
     g = torch.Generator().manual_seed(seed)
     sd = model.state_dict()
+    bound = 1.0
     for k, v in sd.items():
         if k == "quantize.embedding.weight":
             v.copy_(torch.randn(v.shape, generator=g))
         elif ".norm" in k:
             v.copy_((1.0 if k.endswith("weight") else 0.0) + 0.1 * torch.randn(v.shape, generator=g))
+        else:
+            if k.endswith(".weight"):
+                bound = 1.0 / float(np.prod(v.shape[1:])) ** 0.5
+            v.copy_((torch.rand(v.shape, generator=g) * 2 - 1) * bound)
     model.load_state_dict(sd)
     return model
