@@ -105,6 +105,17 @@ size_t sgam_vq_workspace_bytes(int T);
 int sgam_vq_nearest(const float *z, const float *codebook, int T, int n_e, int D, void *best,
                     int64_t *idx, float *z_q, float *dmin, void *stream);
 
+/* Tensor-core variant of the same search (bit-identical idx / z_q / dmin): approximate distances on tcgen05 (split
+ * bf16, fp32 accumulate) reduced to one minimum per (token, 128-code tile), then the tiles within a proven error
+ * slack of the best are re-evaluated in the canonical fp32 order.  z_hi/z_lo, e_hi/e_lo: split-bf16 planes of z and
+ * the codebook (sgam_split_bf16); ee [n_e] = canonical squared code norms (sgam_vq_norms, cacheable per codebook),
+ * ee_max = max(ee); workspace: sgam_vq_tc_workspace_bytes(T, n_e).  D % 64 == 0, n_e % 128 == 0. */
+int sgam_vq_norms(const float *x, float *out, int rows, int D, void *stream);
+size_t sgam_vq_tc_workspace_bytes(int T, int n_e);
+int sgam_vq_nearest_tc(const float *z, const void *z_hi, const void *z_lo, const float *codebook, const void *e_hi,
+                       const void *e_lo, const float *ee, float ee_max, int T, int n_e, int D, void *workspace,
+                       int64_t *idx, float *z_q, float *dmin, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage (iii): VQGAN encoder / decoder operators (sgam/generative_sensing_module/modules/
  * diffusionmodules/model.py).  Activations are NHWC inside the network.

@@ -128,6 +128,10 @@ struct TcParams {
     __nv_bfloat16 *D_hi, *D_lo; // split-bf16 output (or null)
     float *stats;               // or null: GroupNorm partial sums per (batch, 128-pixel block) [B][blocks][32][2]
     int cpg;                    // channels per group = N / 32 when stats != null
+    // VQ mode (vq_tilemin != null): no D; the epilogue forms d = (zz[m] + ee[n]) - 2*acc and keeps the per-row minimum
+    // over the tile's columns: vq_tilemin[m * tiles_n + n_tile]
+    const float *vq_zz, *vq_ee;
+    float *vq_tilemin;
 };
 
 // per-warp GroupNorm partial sums of one 32-column chunk: CPG channels per group, rows = lanes
@@ -272,6 +276,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 const long long m = (long long)oy * p.Wo + ox;          // row within the batch slice
                 const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
                 const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
+                if (p.vq_tilemin) {                               // codebook search: per-row minimum of the approximate distances
+                    const float zz = row_ok ? __ldg(p.vq_zz + m) : 0.0f;
+                    float best = INFINITY;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * BN + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(p.vq_ee + n0 + c0 + j));
+                            best = fminf(best, fminf(fminf((zz + e4.x) - 2.0f * __uint_as_float(v[j]), (zz + e4.y) - 2.0f * __uint_as_float(v[j + 1])),
+                                                     fminf((zz + e4.z) - 2.0f * __uint_as_float(v[j + 2]), (zz + e4.w) - 2.0f * __uint_as_float(v[j + 3]))));
+                        }
+                    }
+                    if (row_ok) p.vq_tilemin[m * p.tiles_n + (tile % p.tiles_n)] = best;
+                    continue;
+                }
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t v[32];
@@ -403,13 +424,14 @@ int sm_count_cached() {
     return n;
 }
 
-// Kernel variant: SGAM_TC_VARIANT = 0 (BK 64, 3 stages), 1 (BK 32, deeper ring), 2 (BK 32, two pixel blocks per weight tile)
+// Kernel variant: SGAM_TC_VARIANT = 0 (BK 64, 3 stages), 1 (BK 32, deeper ring), 2 (BK 32, two pixel blocks per weight tile),
+// 3 (as 0, plus 256-column tiles where N % 256 == 0 and the grid stays full: A amortised over twice the columns)
 int tc_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("SGAM_TC_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 0 || v > 2) v = 0;
+        if (v < 0 || v > 3) v = 0;
     }
     return v;
 }
@@ -436,6 +458,10 @@ TilePlan plan_tiles(int B, int Ho, int Wo, int N) {
     t.BN = pick_bn(tiles1, N);
     t.BK = 64; t.MT = 1; t.BW = BW1; t.BH = BH1;
     const int v = tc_variant();
+    if (v == 3) {
+        if (t.BN == 128 && N % 256 == 0 && tiles1 * (N / 256) >= 2LL * sm_count_cached()) t.BN = 256;
+        return t;
+    }
     if (v >= 1 && t.BN >= 64) t.BK = 32;
     if (v == 2 && t.BN >= 64) {
         // two 128-pixel blocks per tile when the grid stays full and the blocks tile the image exactly
@@ -465,6 +491,7 @@ int launch_tc(const TilePlan &t, const CUtensorMap &a_hi, const CUtensorMap &a_l
               TcParams p, int tiles_m, int Npad, cudaStream_t s) {
     p.tiles_m = tiles_m;
     p.tiles_n = cdiv(Npad, t.BN);
+    if (t.BN == 256) return launch_cfg<256, 64, 2, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
     if (t.BN == 128 && t.BK == 64) return launch_cfg<128, 64, 3, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
     if (t.BN == 64 && t.BK == 64) return launch_cfg<64, 64, 4, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
     if (t.BN == 32) return launch_cfg<32, 64, 4, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
@@ -545,4 +572,26 @@ extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const voi
     p.bias_n = nullptr; p.bias_m = bias_m; p.R = nullptr; p.D = C; p.D_hi = (__nv_bfloat16 *)c_hi; p.D_lo = (__nv_bfloat16 *)c_lo;
     p.stats = nullptr; p.cpg = 0;
     return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, p.tiles_x * batch, N, (cudaStream_t)stream);
+}
+
+// Approximate squared distances of T tokens to n_e codes on tensor cores, reduced to one minimum per (token, 128-code
+// tile).  Called by sgam_vq_nearest_tc (vq.cu), which re-evaluates the candidate tiles in the canonical fp32 order.
+int sgam_vq_tilemin_launch(const void *z_hi, const void *z_lo, const void *e_hi, const void *e_lo, const float *zz, const float *ee,
+                           float *tilemin, int T, int n_e, int D, cudaStream_t stream) {
+    TilePlan t{128, 64, 1, 128, 1};
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    const long long adims[4] = {D, T, 1, 1};
+    const int abox[4] = {t.BK, 128, 1, 1};
+    const long long bdims[3] = {D, n_e, 1};
+    const int bbox[3] = {t.BK, t.BN, 1};
+    int rc;
+    if ((rc = make_map(&a_hi, z_hi, 4, adims, abox)) || (rc = make_map(&a_lo, z_lo, 4, adims, abox)) ||
+        (rc = make_map(&b_hi, e_hi, 3, bdims, bbox)) || (rc = make_map(&b_lo, e_lo, 3, bdims, bbox)))
+        return rc;
+    TcParams p{};
+    p.tiles_x = cdiv(T, 128); p.tiles_y = 1; p.BW = 128; p.BH = 1; p.Ho = 1; p.Wo = T;
+    p.taps = 1; p.ks = 1; p.pad = 0; p.stride = 1; p.kblocks_per_tap = cdiv(D, t.BK); p.N = n_e; p.n_valid = n_e; p.nsplit = 3;
+    p.a_batched = 0; p.b_batched = 0; p.d_batch_stride = 0; p.alpha = 1.0f;
+    p.vq_zz = zz; p.vq_ee = ee; p.vq_tilemin = tilemin;
+    return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, p.tiles_x, n_e, stream);
 }

@@ -146,6 +146,43 @@ def vq_nearest(z_tokens, codebook, want_dmin=False, workspace=None):
     return (idx, z_q, dmin) if want_dmin else (idx, z_q)
 
 
+def vq_norms(x):
+    """Canonical (sequential fma) squared row norms of x [R,D]."""
+    lib = _lib.load()
+    _chk(x, name="x")
+    out = torch.empty(x.shape[0], device=x.device)
+    _lib.check(lib.sgam_vq_norms(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream()), "sgam_vq_norms")
+    return out
+
+
+class CodebookTC:
+    """Per-codebook constants of the tensor-core search: split-bf16 planes, canonical norms and their maximum."""
+
+    def __init__(self, codebook):
+        self.E = _chk(codebook, name="codebook")
+        self.hi, self.lo = split_weight(codebook)
+        self.ee = vq_norms(codebook)
+        self.ee_max = float(self.ee.max().item())
+
+
+def vq_nearest_tc(z_tokens, cb, want_dmin=False):
+    """Tensor-core codebook search; same results as vq_nearest (bit-identical idx, z_q, dmin)."""
+    lib = _lib.load()
+    _chk(z_tokens, name="z")
+    T, D = z_tokens.shape
+    n_e = cb.E.shape[0]
+    dev = z_tokens.device
+    z_hi, z_lo = split_bf16(z_tokens.view(1, 1, T, D))
+    ws = torch.empty(lib.sgam_vq_tc_workspace_bytes(T, n_e) // 4, device=dev)
+    idx = torch.empty(T, dtype=torch.int64, device=dev)
+    z_q = torch.empty(T, D, device=dev)
+    dmin = torch.empty(T, device=dev) if want_dmin else None
+    _lib.check(lib.sgam_vq_nearest_tc(z_tokens.data_ptr(), z_hi.data_ptr(), z_lo.data_ptr(), cb.E.data_ptr(), cb.hi.data_ptr(),
+                                      cb.lo.data_ptr(), cb.ee.data_ptr(), cb.ee_max, T, n_e, D, ws.data_ptr(), idx.data_ptr(),
+                                      z_q.data_ptr(), _ptr(dmin), _stream()), "sgam_vq_nearest_tc")
+    return (idx, z_q, dmin) if want_dmin else (idx, z_q)
+
+
 # -------------------------------------------------------------------------------------------- stage (iii)
 def stem_conv(x, mask, w, bias):
     """cat(x, mask) -> 1x1 conv 5->4 (model.py:106-113).  x [B,4,H,W] NCHW -> [B,H,W,4] NHWC."""

@@ -55,7 +55,10 @@ class VQGANEngine:
         self.p = p
         self.n_embed, self.embed_dim = p["quantize.embedding.weight"].shape
         self.wsplit = {}
+        self.codebook_tc = None
         if self.mode == "tc":
+            if self.embed_dim % 64 == 0 and self.n_embed % 128 == 0:
+                self.codebook_tc = ops.CodebookTC(p["quantize.embedding.weight"])
             for k, v in p.items():
                 if k.endswith(".weight") and v.dim() == 2 and k != "quantize.embedding.weight" and v.shape[1] % 64 == 0:
                     self.wsplit[k[:-len(".weight")]] = ops.split_weight(v, pad_rows_to=32)
@@ -186,7 +189,10 @@ class VQGANEngine:
     def quantize(self, pre_quant):
         """quantize.py:275-319 / :344-381 (topk=1): NHWC latent -> idx [B,h,w] int64, z_q NHWC."""
         B, h, w, D = pre_quant.shape
-        idx, z_q = ops.vq_nearest(pre_quant.view(B * h * w, D), self.p["quantize.embedding.weight"])
+        if self.codebook_tc is not None:
+            idx, z_q = ops.vq_nearest_tc(pre_quant.view(B * h * w, D), self.codebook_tc)
+        else:
+            idx, z_q = ops.vq_nearest(pre_quant.view(B * h * w, D), self.p["quantize.embedding.weight"])
         return idx.view(B, h, w), z_q.view(B, h, w, D)
 
     def decode(self, z_q):

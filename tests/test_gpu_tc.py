@@ -216,3 +216,46 @@ def test_tc_network_512_config5_shape(engines, state_dicts):
     assert same.float().mean().item() >= 0.995, f"{(~same).sum().item()} of 1024 tokens differ"
     if same.all():
         assert rel(dec, dec_o) < 1e-3
+
+
+@pytest.mark.parametrize("ds", ["clevr-infinite", "google_earth"])
+def test_vq_tensor_core_search_is_bit_identical(ops, golden, state_dicts, ds):
+    """Stage (ii) on tensor cores: approximate tile minima + canonical re-evaluation == the canonical kernel == oracle."""
+    from oracle import native
+    E = state_dicts(ds)["quantize.embedding.weight"].cuda()
+    cb = ops.CodebookTC(E)
+    rng = np.random.default_rng(41)
+    z = rng.standard_normal((1, 256, 16, 16)).astype(np.float32) * 0.9
+    zt = torch.from_numpy(np.ascontiguousarray(z.transpose(0, 2, 3, 1).reshape(-1, 256))).cuda()
+    idx, zq, dmin = ops.vq_nearest_tc(zt, cb, want_dmin=True)
+    idx_s, zq_s, dmin_s = ops.vq_nearest(zt, E, want_dmin=True)
+    assert torch.equal(idx, idx_s) and torch.equal(zq, zq_s) and torch.equal(dmin, dmin_s)
+    assert np.array_equal(idx.cpu().numpy().reshape(16, 16), golden[f"vq.{ds}.idx"])
+    o_idx, o_dmin, _ = native.vq_nearest(zt.cpu().numpy(), E.cpu().numpy())
+    assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(dmin.cpu().numpy(), o_dmin)
+
+
+def test_vq_tensor_core_search_hard_cases(ops):
+    rng = np.random.default_rng(3)
+    # exact ties across tiles (duplicated codes 4096 apart), ragged T
+    E = rng.standard_normal((8192, 256)).astype(np.float32)
+    E[4096:] = E[:4096]
+    z = (E[rng.integers(0, 4096, 77)] + 0.01 * rng.standard_normal((77, 256))).astype(np.float32)
+    Ed, zd = torch.from_numpy(E).cuda(), torch.from_numpy(z).cuda()
+    idx, zq = ops.vq_nearest_tc(zd, ops.CodebookTC(Ed))
+    idx_s, zq_s = ops.vq_nearest(zd, Ed)
+    assert torch.equal(idx, idx_s) and idx.max().item() < 4096
+    # the reference's default U(+-1/n_e) init: every tile is a candidate (ill-conditioned minima), still identical
+    E = rng.uniform(-1 / 4096, 1 / 4096, (4096, 256)).astype(np.float32)
+    z = rng.standard_normal((300, 256)).astype(np.float32)
+    Ed, zd = torch.from_numpy(E).cuda(), torch.from_numpy(z).cuda()
+    idx, zq, dmin = ops.vq_nearest_tc(zd, ops.CodebookTC(Ed), want_dmin=True)
+    idx_s, zq_s, dmin_s = ops.vq_nearest(zd, Ed, want_dmin=True)
+    assert torch.equal(idx, idx_s) and torch.equal(dmin, dmin_s)
+    # large batch of tokens (8 trajectories), big-norm latents
+    E = rng.standard_normal((16384, 256)).astype(np.float32)
+    z = (rng.standard_normal((2048, 256)) * 3).astype(np.float32)
+    Ed, zd = torch.from_numpy(E).cuda(), torch.from_numpy(z).cuda()
+    idx, zq = ops.vq_nearest_tc(zd, ops.CodebookTC(Ed))
+    idx_s, zq_s = ops.vq_nearest(zd, Ed)
+    assert torch.equal(idx, idx_s) and torch.equal(zq, zq_s)

@@ -30,6 +30,36 @@ for (B_, H, W, Cin, Cout, ks) in [(1, 16, 16, 128, 128, 3), (2, 32, 32, 128, 256
     got = y.permute(0, 3, 1, 2).cpu()
     got2 = (yh.float() + yl.float()).permute(0, 3, 1, 2).cpu()
     print(f"B={B_} H={H} W={W} Cin={Cin} Cout={Cout} k={ks}: rel={rel(got, ref):.3e} split-out rel={rel(got2, ref):.3e}", flush=True)
+def bench_conv(B_, H, W, Cin, Cout, ks):
+    x = torch.randn(B_, H, W, Cin, device=dev); w = torch.randn(Cout, ks * ks * Cin, device=dev) / 34; bias = torch.zeros(Cout, device=dev)
+    xs = ops.split_bf16(x); ws = ops.split_weight(w)
+    for _ in range(3): ops.conv2d_tc(xs, ws, bias, ksize=ks)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): ops.conv2d_tc(xs, ws, bias, ksize=ks)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    fl = 2.0 * B_ * H * W * Cout * ks * ks * Cin
+    print(f"conv B={B_} {H}x{W} {Cin}->{Cout} k{ks}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s algorithmic", flush=True)
+
+def bench_gemm(batch, M, N, K, split_out=False):
+    A = torch.randn(batch, M, K, device=dev); Bm = torch.randn(batch, N, K, device=dev)
+    a = ops.split_weight(A); b = ops.split_weight(Bm)
+    kw = dict(out_f32=not split_out, out_split=split_out)
+    for _ in range(3): ops.gemm_nt_tc(a, b, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): ops.gemm_nt_tc(a, b, **kw)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"gemm batch={batch} M={M} N={N} K={K} split_out={split_out}: {ms:.3f} ms  {2.0*batch*M*N*K/ms/1e9:.1f} TFLOP/s algorithmic", flush=True)
+
+bench_conv(8, 64, 64, 256, 256, 3)
+bench_conv(8, 32, 32, 256, 256, 3)
+bench_conv(8, 16, 16, 512, 512, 3)
+bench_conv(8, 64, 64, 256, 256, 1)
+bench_gemm(8, 4096, 4096, 256)
+bench_gemm(8, 4096, 256, 4096, split_out=True)
 print("== timing 128ch 256x256 3x3, batch 8 ==", flush=True)
 x = torch.randn(8, 256, 256, 128, device=dev); w = torch.randn(128, 1152, device=dev) / 34; bias = torch.zeros(128, device=dev)
 xs = ops.split_bf16(x); ws = ops.split_weight(w)
