@@ -157,6 +157,11 @@ int sgam_softmax_rows(float *x, long long rows, int cols, void *stream);
  * sgam_groupnorm / sgam_gemm_nt / sgam_softmax_rows).
  */
 
+/* Stem for the tensor-core path: as sgam_stem_conv, but the [B,H,W,4] result is written as split bf16 with the channel
+ * dimension zero-padded to Cpad (64), so that encoder.conv_in (Cin = 4) runs as a K = 9*Cpad tensor-core GEMM. */
+int sgam_stem_conv_split(const float *x, const uint8_t *mask, const float *w, const float *bias, int B, int H, int W,
+                         int Cpad, void *hi, void *lo, void *stream);
+
 /* fp32 NHWC [B,H,W,C] -> hi / lo bf16 [B,H<<up,W<<up,C] (nearest x2 up-sampling fused: Upsample, model.py:50). */
 int sgam_split_bf16(const float *x, void *hi, void *lo, int B, int H, int W, int C, int upsample, void *stream);
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     "sgam_groupnorm": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p]),
     "sgam_gemm_nt": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_ll, c_ll, c_ll, c_f, c_p]),
     "sgam_softmax_rows": (c_i, [c_p, c_ll, c_i, c_p]),
+    "sgam_stem_conv_split": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "sgam_split_bf16": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sgam_groupnorm_split": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p]),
     "sgam_softmax_split": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_p]),

@@ -134,6 +134,35 @@ softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi
     }
 }
 
+// VQModel.encode stem for the tensor-core path: cat(x, mask) -> 1x1 conv 5 -> 4 (model.py:106-113), written as split
+// bf16 NHWC with the 4 channels zero-padded to CP (64) so that encoder.conv_in (3x3, Cin = 4) runs as a K = 9*64 GEMM.
+__global__ void __launch_bounds__(256)
+stem_split_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask, const float *__restrict__ w,
+                  const float *__restrict__ bias, int HW, int CP, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (p >= HW) return;
+    float in[5];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) in[c] = x[((size_t)b * 4 + c) * HW + p];
+    in[4] = mask ? (mask[(size_t)b * HW + p] ? 1.0f : 0.0f) : 0.0f;
+    float o[4];
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+        float a = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) a = fmaf(in[c], __ldg(w + co * 5 + c), a);
+        o[co] = a + __ldg(bias + co);
+    }
+    uint32_t h[2], l[2];
+    split2(o[0], o[1], h[0], l[0]);
+    split2(o[2], o[3], h[1], l[1]);
+    uint4 *dh = reinterpret_cast<uint4 *>(hi + ((size_t)b * HW + p) * CP), *dl = reinterpret_cast<uint4 *>(lo + ((size_t)b * HW + p) * CP);
+    dh[0] = make_uint4(h[0], h[1], 0u, 0u);
+    dl[0] = make_uint4(l[0], l[1], 0u, 0u);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int k = 1; k < CP / 8; ++k) { dh[k] = z; dl[k] = z; }
+}
+
 // reduce the per-pixel-block partial sums written by tc_gemm_kernel's epilogue: [B][tiles][32][2] fp32 -> mean, rstd
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrstd, int tiles, double count) {
@@ -160,6 +189,15 @@ gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrs
 
 // gn_stats launcher lives in net_simt.cu
 int sgam_gn_stats_launch(const float *x, double *partial, int B, long long HW, int C, cudaStream_t s);
+
+extern "C" int sgam_stem_conv_split(const float *x, const uint8_t *mask, const float *w, const float *bias, int B, int H, int W,
+                                    int Cpad, void *hi, void *lo, void *stream) {
+    SGAM_REQUIRE(x && w && bias && hi && lo && B > 0 && H > 0 && W > 0 && Cpad >= 8 && Cpad % 8 == 0, "stem_conv_split: bad arguments");
+    dim3 grid(cdiv((long long)H * W, 256), B);
+    stem_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mask, w, bias, H * W, Cpad, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
 
 extern "C" int sgam_split_bf16(const float *x, void *hi, void *lo, int B, int H, int W, int C, int upsample, void *stream) {
     SGAM_REQUIRE(x && hi && lo && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "split_bf16: bad arguments");

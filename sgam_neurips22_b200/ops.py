@@ -274,6 +274,19 @@ def _bf16_pair(shape, device):
     return (torch.empty(shape, dtype=torch.bfloat16, device=device), torch.empty(shape, dtype=torch.bfloat16, device=device))
 
 
+def stem_conv_split(x, mask, w, bias, cpad=64):
+    """Stem (model.py:106-113) -> split bf16 NHWC [B,H,W,cpad] with channels 4.. zero (feeds the tensor-core conv_in)."""
+    lib = _lib.load()
+    _chk(x, name="x"), _chk(w, name="w"), _chk(bias, name="bias")
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    B, _, H, W = x.shape
+    hi, lo = _bf16_pair((B, H, W, cpad), x.device)
+    _lib.check(lib.sgam_stem_conv_split(x.data_ptr(), _ptr(mask), w.data_ptr(), bias.data_ptr(), B, H, W, cpad, hi.data_ptr(),
+                                        lo.data_ptr(), _stream()), "sgam_stem_conv_split")
+    return hi, lo
+
+
 def split_bf16(x, upsample=0):
     """fp32 NHWC [B,H,W,C] -> (hi, lo) bf16 [B,H<<up,W<<up,C] with x = hi + lo (+ fused nearest x2 up-sampling)."""
     lib = _lib.load()

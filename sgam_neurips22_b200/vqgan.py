@@ -62,6 +62,13 @@ class VQGANEngine:
             for k, v in p.items():
                 if k.endswith(".weight") and v.dim() == 2 and k != "quantize.embedding.weight" and v.shape[1] % 64 == 0:
                     self.wsplit[k[:-len(".weight")]] = ops.split_weight(v, pad_rows_to=32)
+            # encoder.conv_in has Cin = 4: zero-pad each tap's channels to 64 so it runs on the tensor cores as well
+            w = p["encoder.conv_in.weight"]
+            cin = self.dd["in_channels"]
+            if w.shape[1] == 9 * cin and cin <= 64:
+                wp = torch.zeros(w.shape[0], 9, 64, device=w.device)
+                wp[:, :, :cin] = w.view(w.shape[0], 9, cin)
+                self.wsplit["encoder.conv_in.padded"] = ops.split_weight(wp.view(w.shape[0], 9 * 64).contiguous(), pad_rows_to=32)
 
     def has(self, name):
         return f"{name}.weight" in self.p
@@ -141,8 +148,7 @@ class VQGANEngine:
     def encoder(self, h):
         dd = self.dd
         nres, nrb = len(dd["ch_mult"]), dd["num_res_blocks"]
-        h = self.conv("encoder.conv_in", h, ksize=3)                      # Cin = 4: fp32 kernel
-        for l in range(nres):
+        for l in range(nres):                                             # h = encoder.conv_in(stem(x)), see encode()
             for b in range(nrb):
                 h = self.resnet_block(f"encoder.down.{l}.block.{b}", h)
                 if self.has(f"encoder.down.{l}.attn.{b}.norm"):
@@ -182,7 +188,14 @@ class VQGANEngine:
         """model.py:106-116: x [B,4,H,W] NCHW (+ mask [B,1,H,W] uint8) -> pre-quantised latent NHWC [B,h,w,D]."""
         if mask is not None:
             mask = mask.reshape(mask.shape[0], *mask.shape[-2:])
-        h = ops.stem_conv(x, mask, self.p["conv_in.weight"], self.p["conv_in.bias"])
+        B, _, H, W = x.shape
+        if self.mode == "tc" and "encoder.conv_in.padded" in self.wsplit and \
+                ops.tc_supported_conv(H, W, 64, self.p["encoder.conv_in.weight"].shape[0], 3, 1):
+            xs = ops.stem_conv_split(x, mask, self.p["conv_in.weight"], self.p["conv_in.bias"], 64)
+            h = ops.conv2d_tc(xs, self.wsplit["encoder.conv_in.padded"], self.p["encoder.conv_in.bias"], ksize=3,
+                              nsplit=self.nsplit, gn_stats=True)
+        else:
+            h = self.conv("encoder.conv_in", ops.stem_conv(x, mask, self.p["conv_in.weight"], self.p["conv_in.bias"]), ksize=3)
         h = self.encoder(h)
         return self.conv_from_f32("quant_conv", h, 1)
 
