@@ -457,7 +457,7 @@ extern "C" int sgam_gemm_nt(const float *A, const float *Bm, float *C, const flo
 }
 
 extern "C" int sgam_gn_splits(long long HW) {
-    long long s = HW / 512;
+    long long s = HW / 8;               // >= 8 pixels per block, at most 128 blocks per batch element
     return (int)(s < 1 ? 1 : (s > 128 ? 128 : s));
 }
 

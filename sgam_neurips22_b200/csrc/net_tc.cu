@@ -132,6 +132,11 @@ struct TcParams {
     // over the tile's columns: vq_tilemin[m * tiles_n + n_tile]
     const float *vq_zz, *vq_ee;
     float *vq_tilemin;
+    // split-K (ksplit > 1): tile id gains a k-split index (fastest); each split accumulates kb_per_split k-blocks and
+    // stores its raw fp32 partial tile to splitk_ws[split][B*M][N]; splitk_reduce_kernel adds them in split order.
+    int ksplit, kb_per_split;
+    float *splitk_ws;
+    long long split_stride;
 };
 
 // per-warp GroupNorm partial sums of one 32-column chunk: CPG channels per group, rows = lanes
@@ -175,7 +180,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.taps * p.kblocks_per_tap;
-    const int total_tiles = p.tiles_m * p.tiles_n;
+    const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -197,12 +202,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_PLANE + B_PLANE);
             int kbg = 0;                                              // k-block counter across tiles (ring position)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n0 = (tile % p.tiles_n) * BN;
-                int t = tile / p.tiles_n;
+                const int ksp = tile % p.ksplit, mn = tile / p.ksplit;
+                const int kb0 = ksp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                const int n0 = (mn % p.tiles_n) * BN;
+                int t = mn / p.tiles_n;
                 const int tx = t % p.tiles_x; t /= p.tiles_x;
                 const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
                 const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+                for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
                     const int s = kbg % STAGES, it = kbg / STAGES;
                     mbar_wait(&empty_bar[s], (it & 1) ^ 1);
                     uint8_t *st = smem + (size_t)s * STAGE_BYTES;
@@ -226,9 +233,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             int kbg = 0, li = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
                 const int acc = li & 1;
+                const int ksp = tile % p.ksplit;
+                const int kb0 = ksp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 mbar_wait(&tmem_empty_bar[acc], ((li >> 1) & 1) ^ 1);     // epilogue has drained this accumulator set
                 tc_fence_after();
-                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+                for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
                     const int s = kbg % STAGES, it = kbg / STAGES;
                     mbar_wait(&full_bar[s], it & 1);
                     tc_fence_after();
@@ -242,7 +251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {        // UMMA_K = 16 bf16 = 32 B: advance the start address field by 2
                             const uint64_t off = (uint64_t)(k * 2);
-                            umma_bf16(tmem_d, a_hi + off, b_hi + off, idesc, (kb | k) ? 1u : 0u);
+                            umma_bf16(tmem_d, a_hi + off, b_hi + off, idesc, (kb != kb0 || k) ? 1u : 0u);
                             if (p.nsplit == 3) {
                                 umma_bf16(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
                                 umma_bf16(tmem_d, a_lo + off, b_hi + off, idesc, 1u);
@@ -260,8 +269,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         int li = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
             const int acc = li & 1;
-            const int n0 = (tile % p.tiles_n) * BN;
-            int t = tile / p.tiles_n;
+            const int ksp = tile % p.ksplit, mn = tile / p.ksplit;
+            const int n0 = (mn % p.tiles_n) * BN;
+            int t = mn / p.tiles_n;
             const int m_tile = t % (p.tiles_x * p.tiles_y);
             const int tx = t % p.tiles_x; t /= p.tiles_x;
             const int ty = t % p.tiles_y; const int b = t / p.tiles_y;
@@ -290,7 +300,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                                                      fminf((zz + e4.z) - 2.0f * __uint_as_float(v[j + 2]), (zz + e4.w) - 2.0f * __uint_as_float(v[j + 3]))));
                         }
                     }
-                    if (row_ok) p.vq_tilemin[m * p.tiles_n + (tile % p.tiles_n)] = best;
+                    if (row_ok) p.vq_tilemin[m * p.tiles_n + (mn % p.tiles_n)] = best;
+                    continue;
+                }
+                if (p.ksplit > 1) {                               // raw partial sums; bias / residual / statistics happen in the reduce kernel
+                    float *dst = p.splitk_ws + (long long)ksp * p.split_stride + row_off + n0;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * BN + c0), v);
+                        if (row_ok && n0 + c0 < p.n_valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                                        __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        }
+                    }
                     continue;
                 }
 #pragma unroll 1
@@ -472,6 +497,39 @@ TilePlan plan_tiles(int B, int Ho, int Wo, int N) {
     return t;
 }
 
+// Deterministic split-K reduction: D = sum_s ws[s] (in split order) + bias (+ residual); fp32 NHWC rows of N columns.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float *__restrict__ ws, long long split_stride, int ksplit, const float *__restrict__ bias,
+                     const float *__restrict__ R, float *__restrict__ D, long long total_q, int NQ) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_q; e += (long long)gridDim.x * blockDim.x) {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(ws) + e);
+        for (int s = 1; s < ksplit; ++s) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (long long)s * split_stride) + e);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias) + (int)(e % NQ));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        if (R) {
+            const float4 r = __ldg(reinterpret_cast<const float4 *>(R) + e);
+            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+        }
+        reinterpret_cast<float4 *>(D)[e] = a;
+    }
+}
+
+// Split the K loop when the (pixel block x column tile) grid would leave most SMs idle (low-resolution layers,
+// single-trajectory batches): returns the number of splits (1 = none).
+int pick_ksplit(long long mn_tiles, int num_kb) {
+    const int sms = sm_count_cached();
+    if (mn_tiles * 2 > sms || num_kb < 8) return 1;
+    int want = (int)(sms / mn_tiles);
+    int per = (num_kb + want - 1) / want;
+    if (per < 4) per = 4;
+    return (num_kb + per - 1) / per;
+}
+
 template <int BN, int BK, int STAGES, int MT>
 int launch_cfg(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, const TcParams &p, cudaStream_t s) {
     using Cfg = TcCfg<BN, BK, STAGES, MT>;
@@ -480,7 +538,7 @@ int launch_cfg(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorM
         SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<BN, BK, STAGES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
-    const int total = p.tiles_m * p.tiles_n;
+    const int total = p.tiles_m * p.tiles_n * p.ksplit;
     const int grid = total < sm_count_cached() ? total : sm_count_cached();      // persistent: one CTA per SM
     tc_gemm_kernel<BN, BK, STAGES, MT><<<grid, TC_THREADS, Cfg::SMEM, s>>>(a_hi, a_lo, b_hi, b_lo, p);
     SGAM_LAUNCH_OK();
@@ -491,6 +549,7 @@ int launch_tc(const TilePlan &t, const CUtensorMap &a_hi, const CUtensorMap &a_l
               TcParams p, int tiles_m, int Npad, cudaStream_t s) {
     p.tiles_m = tiles_m;
     p.tiles_n = cdiv(Npad, t.BN);
+    if (p.ksplit < 1) { p.ksplit = 1; p.kb_per_split = p.taps * p.kblocks_per_tap; }
     if (t.BN == 256) return launch_cfg<256, 64, 2, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
     if (t.BN == 128 && t.BK == 64) return launch_cfg<128, 64, 3, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
     if (t.BN == 64 && t.BK == 64) return launch_cfg<64, 64, 4, 1>(a_hi, a_lo, b_hi, b_lo, p, s);
@@ -514,7 +573,7 @@ extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize
 
 extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                               const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
-                              int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, void *stream) {
+                              int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws, void *stream) {
     SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && (y || (y_hi && y_lo)), "conv2d_tc: null pointer");
     SGAM_REQUIRE(!gn_partial || (Cout % 128 == 0 && Cout <= 512 && !out_nchw), "conv2d_tc: fused GroupNorm statistics need Cout in {128,256,384,512}");
     SGAM_REQUIRE(stride == 1 || stride == 2, "conv2d_tc: stride %d", stride);
@@ -544,7 +603,35 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
     p.a_batched = 1; p.b_batched = 0; p.d_batch_stride = (long long)Ho * Wo * Cout; p.alpha = 1.0f;
     p.bias_n = bias; p.bias_m = nullptr; p.R = residual; p.D = y; p.D_hi = (__nv_bfloat16 *)y_hi; p.D_lo = (__nv_bfloat16 *)y_lo;
     p.stats = gn_partial; p.cpg = Cout / 32;
-    return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, p.tiles_x * p.tiles_y * B, Npad, (cudaStream_t)stream);
+    const int tiles_m = p.tiles_x * p.tiles_y * B, num_kb = taps * p.kblocks_per_tap;
+    const int ksplit = (splitk_ws && y && !y_hi && !out_nchw && Npad == Cout && !gn_partial) ? pick_ksplit((long long)tiles_m * cdiv(Npad, t.BN), num_kb) : 1;
+    if (ksplit > 1) {
+        p.ksplit = ksplit; p.kb_per_split = cdiv(num_kb, ksplit); p.ksplit = cdiv(num_kb, p.kb_per_split);
+        p.splitk_ws = splitk_ws; p.split_stride = (long long)B * Ho * Wo * Cout;
+        int rc2 = launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, (cudaStream_t)stream);
+        if (rc2) return rc2;
+        const long long total_q = p.split_stride / 4;
+        const unsigned blocks = (unsigned)min((long long)148 * 4, (total_q + 255) / 256);
+        splitk_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(splitk_ws, p.split_stride, p.ksplit, bias, residual, y, total_q, Cout / 4);
+        SGAM_LAUNCH_OK();
+        return SGAM_OK;
+    }
+    return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, (cudaStream_t)stream);
+}
+
+// Workspace (floats) sgam_conv2d_tc wants for split-K on this shape; 0 = the K loop will not be split.
+extern "C" long long sgam_conv2d_tc_splitk_floats(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
+    if (stride != 1 && stride != 2) return 0;
+    const int Ho = H / stride, Wo = W / stride;
+    if (Ho <= 0 || Wo <= 0 || !sgam_tc_supported_conv(Ho, Wo, Cin, Cout, ksize, stride) || Cout % 32) return 0;
+    TilePlan t = plan_tiles(B, Ho, Wo, Cout);
+    if (stride == 2 && t.MT == 2) { t.MT = 1; t.BW = Wo >= 128 ? 128 : Wo; t.BH = 128 / t.BW; }
+    const long long tiles = (long long)cdiv(Wo, t.BW) * cdiv(Ho, t.BH) * B * cdiv(Cout, t.BN);
+    const int num_kb = ksize * ksize * (Cin / t.BK);
+    const int ks = pick_ksplit(tiles, num_kb);
+    if (ks <= 1) return 0;
+    const int per = cdiv(num_kb, ks);
+    return (long long)cdiv(num_kb, per) * B * Ho * Wo * Cout;
 }
 
 extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const void *b_hi_p, const void *b_lo_p, const float *bias_m,

@@ -363,12 +363,16 @@ def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=
     pair = _bf16_pair((B, Ho, Wo, Cout), x_hi.device) if out_split else (None, None)
     if residual is not None:
         _chk(residual, name="residual")
-    partial = None
-    if gn_stats and out_f32 and not out_nchw and Cout % 128 == 0 and Cout <= 512:
+    partial = splitk = None
+    if out_f32 and not out_split and not out_nchw and Cout % 32 == 0:
+        n_ws = lib.sgam_conv2d_tc_splitk_floats(B, H, W, Cin, Cout, ksize, stride)
+        if n_ws > 0:                    # under-filled grid: split the K loop (statistics then come from the stats kernel)
+            splitk = torch.empty(n_ws, device=x_hi.device)
+    if splitk is None and gn_stats and out_f32 and not out_nchw and Cout % 128 == 0 and Cout <= 512:
         partial = torch.empty(lib.sgam_tc_gn_partial_floats(B, Ho, Wo), device=x_hi.device)
     _lib.check(lib.sgam_conv2d_tc(x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), _ptr(bias),
                                   _ptr(residual), _ptr(y), _ptr(pair[0]), _ptr(pair[1]), B, H, W, Cin, Cout, ksize,
-                                  stride, int(out_nchw), nsplit, _ptr(partial), _stream()), "sgam_conv2d_tc")
+                                  stride, int(out_nchw), nsplit, _ptr(partial), _ptr(splitk), _stream()), "sgam_conv2d_tc")
     if partial is not None:
         y.gn_partial = partial          # GroupNorm statistics of y, fused into the epilogue (consumed by groupnorm_split)
     if out_f32 and out_split:

@@ -192,7 +192,9 @@ def test_groupnorm_statistics_fused_into_conv_epilogue(ops, case):
     xs = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda())
     ws = ops.split_weight(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda(), pad_rows_to=32)
     y = ops.conv2d_tc(xs, ws, bias.cuda(), residual=r.permute(0, 2, 3, 1).contiguous().cuda(), ksize=3, gn_stats=True)
-    assert hasattr(y, "gn_partial")
+    from sgam_neurips22_b200 import _lib
+    splitk = _lib.load().sgam_conv2d_tc_splitk_floats(B, H, W, Cin, Cout, 3, 1) > 0
+    assert hasattr(y, "gn_partial") != splitk          # under-filled grids split K instead and use the statistics kernel
     hi, lo = ops.groupnorm_split(y, ga.cuda(), be.cuda(), True)
     assert rel((hi.float() + lo.float()).permute(0, 3, 1, 2), ref) < 5e-5
     y2 = y.clone()                                             # no fused statistics attached: the stats kernel path
@@ -259,3 +261,22 @@ def test_vq_tensor_core_search_hard_cases(ops):
     idx, zq = ops.vq_nearest_tc(zd, ops.CodebookTC(Ed))
     idx_s, zq_s = ops.vq_nearest(zd, Ed)
     assert torch.equal(idx, idx_s) and torch.equal(zq, zq_s)
+
+
+@pytest.mark.parametrize("case", [(1, 16, 16, 512, 512, 3), (1, 32, 32, 256, 256, 3), (1, 4, 4, 512, 512, 3), (2, 16, 16, 256, 512, 3)])
+def test_conv2d_tc_split_k(ops, case):
+    """Low-resolution layers at small batch: the K loop is split across CTAs and reduced deterministically."""
+    from sgam_neurips22_b200 import _lib
+    B, H, W, Cin, Cout, ks = case
+    assert _lib.load().sgam_conv2d_tc_splitk_floats(B, H, W, Cin, Cout, ks, 1) > 0
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, ks, ks, generator=g) / (Cin * ks * ks) ** 0.5
+    bias, r = torch.randn(Cout, generator=g), torch.randn(B, Cout, H, W, generator=g)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=ks // 2) + r.double()
+    xs = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda())
+    ws = ops.split_weight(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda(), pad_rows_to=32)
+    rr = r.permute(0, 2, 3, 1).contiguous().cuda()
+    y = ops.conv2d_tc(xs, ws, bias.cuda(), residual=rr, ksize=ks)
+    assert rel(y.permute(0, 3, 1, 2), ref) < 5e-5
+    assert torch.equal(y, ops.conv2d_tc(xs, ws, bias.cuda(), residual=rr, ksize=ks))       # deterministic reduction order
