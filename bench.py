@@ -357,6 +357,37 @@ def main():
         single = {"value": world * args.steps / (ms1 / 1000.0), "unit": UNIT, "ms_per_frame": ms1 / args.steps,
                   "note": "one trajectory per GPU (batch 1), inputs resident, CUDA graph"}
 
+    # ---------------- the drop-in scene loop itself (sequential frames of ONE trajectory through InfiniteSceneGeneration) ----
+    scene_loop = None
+    if rank == 0:
+        import tempfile
+        from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration
+        cwd = os.getcwd()
+        os.chdir(tempfile.mkdtemp(prefix="sgam_bench_"))
+        try:
+            rng = np.random.default_rng(0)
+            lo, hi = synthetic.DATASETS[ds]["depth"]
+            yy, xx = np.meshgrid(np.linspace(0, 1, 256), np.linspace(0, 1, 256), indexing="ij")
+            seed = (rng.integers(0, 256, (256, 256, 3)).astype(np.uint8),
+                    (lo + (hi - lo) * (0.5 + 0.3 * np.sin(3 * xx) * np.cos(2 * yy))).astype(np.float32))
+            dim = (5, 6) if ds == "clevr-infinite" else (30, 1)
+            pipe = InfiniteSceneGeneration(model, ds, seed_frame=seed, output_dim=dim)
+            n_loop, skip = dim[0] * dim[1] - 1, 5
+            for i in range(n_loop):
+                if i == skip:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                pipe.one_step_prediction(pipe.next_pose(pipe.curr), save_res_to_disk=False)
+                pipe.curr += 1
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            scene_loop = {"value": (n_loop - skip) / dt, "unit": UNIT, "ms_per_frame": 1000.0 * dt / (n_loop - skip), "frames": n_loop - skip,
+                          "note": "InfiniteSceneGeneration.one_step_prediction, one trajectory, frames generated sequentially from the "
+                                  "device-resident frame store (source selection, pose math, splat, forward, uint8/depth conversion), "
+                                  "no disk writes, wall clock on rank 0"}
+        finally:
+            os.chdir(cwd)
+
     # ---------------- final map all-gather (the only collective; outside the frames/sec region) ----------------------
     poses = torch.zeros(B, 12, dtype=torch.float64)
     ag_ms = None
@@ -398,6 +429,8 @@ def main():
         }
         if single is not None:
             line["single_trajectory"] = single
+        if scene_loop is not None:
+            line["scene_loop"] = scene_loop
         if ag_ms is not None:
             line["allgather_ms"] = ag_ms
             line["allgather_bytes_per_rank"] = int(B * sdist.record_bytes(res, res))

@@ -76,6 +76,9 @@ class VQModel(torch.nn.Module):
         self.use_rgbd_integration = False
         self.splat_policy = ops.SPLAT_LAST_WRITER          # reference semantics; ops.SPLAT_ZMIN = z-buffered splat
         self.engine_mode = os.environ.get("SGAM_ENGINE_MODE", "tc")   # "tc": tcgen05 split-bf16 convs; "simt": exact fp32
+        # forward() replays one CUDA graph per input shape (~340 kernel nodes) instead of launching op by op
+        self.use_cuda_graph = os.environ.get("SGAM_CUDA_GRAPH", "1") != "0"
+        self._graphs = {}
         if monitor is not None:
             self.monitor = monitor
         if remap is not None:
@@ -121,10 +124,12 @@ class VQModel(torch.nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._engine = None            # .to() / .cuda() / .float(): weights moved, repack lazily
+        self._graphs = {}
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         self._engine = None
+        self._graphs = {}
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def init_from_ckpt(self, path, ignore_keys=['loss'], only_keep_keys=[]):
@@ -274,10 +279,51 @@ class VQModel(torch.nn.Module):
         """model.py:136-139 (the reference calls a method VectorQuantizer2 does not have; this is the intent)."""
         return self.engine.decode(self.engine.embed_code(code_b.to(torch.int64)))
 
+    def _graphed_forward(self, x, mask_u8):
+        """encode -> quantize -> decode as one CUDA-graph replay.  -> (dec NCHW, pre NHWC, z_q NHWC, idx), fresh tensors."""
+        eng = self.engine
+        key = (tuple(x.shape), mask_u8 is not None, x.device.index)
+        g = self._graphs.get(key)
+        if g is None:
+            sx = x.clone()
+            sm = mask_u8.clone() if mask_u8 is not None else None
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                eng.forward(sx, sm)                                   # warm-up: allocator, one-time kernel attributes
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = eng.forward(sx, sm)
+            g = self._graphs[key] = (graph, sx, sm, outs)
+        graph, sx, sm, outs = g
+        sx.copy_(x, non_blocking=True)
+        if sm is not None:
+            sm.copy_(mask_u8, non_blocking=True)
+        graph.replay()
+        return tuple(o.clone() for o in outs)
+
     @torch.no_grad()
     def forward(self, input, topk=None, extrapolation_mask=None, sample_number=1, get_codebook_count=False,
                 get_pre_quantized_feature=False, get_quantized_feature=False):
         """model.py:141-167."""
+        if self.use_cuda_graph and self.use_vq() and topk in (None, 1) and sample_number == 1 and input.is_cuda:
+            dec, pre, z_q, idx = self._graphed_forward(input.contiguous(), self._mask_u8(extrapolation_mask))
+            pre_nchw = pre.permute(0, 3, 1, 2)
+            if topk is None:
+                diff = z_q - pre
+                out = [dec, (1.0 + 0.25) * torch.mean(diff * diff)]
+                info, quants = (None, None, idx), z_q.permute(0, 3, 1, 2)
+            else:
+                out = [[dec[None,]], None]
+                info, quants = (None, None, idx.unsqueeze(1)), z_q.permute(0, 3, 1, 2).unsqueeze(1)
+            if get_codebook_count:
+                out.append(info[-1])
+            if get_pre_quantized_feature:
+                out.append(pre_nchw)
+            if get_quantized_feature:
+                out.append(quants)
+            return out
         res = self.encode(input, topk=topk, encoding_indices=None, extrapolation_mask=extrapolation_mask,
                           sample_number=sample_number)
         if not self.use_vq():

@@ -129,3 +129,23 @@ def test_rgbd_integration_branch_with_supplied_depth(models, tmp_path, monkeypat
     pipe.curr += 1
     pipe.one_step_prediction(pipe.next_pose(pipe.curr))                           # second step: two sources available
     assert len(pipe._frames) == 3
+
+
+def test_vqmodel_forward_graph_replay_equals_eager(models):
+    """forward() replays a cached CUDA graph per input shape; results must equal the op-by-op path bit for bit and
+    must not alias between calls."""
+    model = models("google_earth")
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.rand(1, 4, 64, 64, generator=g).cuda() * 2 - 1 for _ in range(3)]
+    ms = [(torch.rand(1, 1, 64, 64, generator=g) < 0.3).cuda() for _ in range(3)]
+    model.use_cuda_graph = False
+    eager = [model(x, topk=1, extrapolation_mask=m, get_pre_quantized_feature=True, get_quantized_feature=True) for x, m in zip(xs, ms)]
+    model.use_cuda_graph = True
+    model._graphs = {}
+    graphed = [model(x, topk=1, extrapolation_mask=m, get_pre_quantized_feature=True, get_quantized_feature=True) for x, m in zip(xs, ms)]
+    assert len(model._graphs) == 1
+    for e, r in zip(eager, graphed):
+        assert torch.equal(e[0][0], r[0][0]) and torch.equal(e[2], r[2]) and torch.equal(e[3], r[3])
+        assert tuple(r[0][0].shape) == (1, 1, 4, 64, 64) and tuple(r[3].shape) == (1, 1, 256, 4, 4)
+    dec_plain, loss = model(xs[0], extrapolation_mask=ms[0])               # topk=None signature (config 1): [dec, emb_loss]
+    assert torch.equal(dec_plain, eager[0][0][0][0]) and loss.dim() == 0
