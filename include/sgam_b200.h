@@ -105,6 +105,19 @@ size_t sgam_vq_workspace_bytes(int T);
 int sgam_vq_nearest(const float *z, const float *codebook, int T, int n_e, int D, void *best,
                     int64_t *idx, float *z_q, float *dmin, void *stream);
 
+/* quantize.py:344-381 get_multiple_codewords for topk > 1: the topk nearest codes per token
+ * (ascending canonical distance), p = softmax(-d_topk), `samples` multinomial draws with replacement from a
+ * counter-based generator keyed by (seed, token, sample), tokens whose nearest-down-sampled extrapolation mask is 0
+ * pinned to the nearest code.  row0_probs = 1 reproduces the reference, which draws every token from token 0's
+ * probabilities (quantize.py:358).  Bit parity with torch's global generator is impossible; parity is distributional.
+ *   mask [images, H, W] u8 or NULL (all extrapolated); token (ly,lx) of image i reads mask[i*mask_bstride + (ly*fy)*mask_w + lx*fx]
+ *   outputs: topk_idx [T,topk] i64, topk_p [T,topk], idx [T,samples] i64, z_q [T,samples,D] */
+size_t sgam_vq_topk_workspace_bytes(int T, int n_e);
+int sgam_vq_topk_sample(const float *z, const float *codebook, const uint8_t *mask, long long mask_bstride, int mask_w,
+                        int fy, int fx, int lat_w, int tokens_per_image, int T, int n_e, int D, int topk, int samples,
+                        unsigned long long seed, int row0_probs, void *workspace, int64_t *topk_idx, float *topk_p,
+                        int64_t *idx, float *z_q, void *stream);
+
 /* Tensor-core variant of the same search (bit-identical idx / z_q / dmin): approximate distances on tcgen05 (split
  * bf16, fp32 accumulate) reduced to one minimum per (token, 128-code tile), then the tiles within a proven error
  * slack of the best are re-evaluated in the canonical fp32 order.  z_hi/z_lo, e_hi/e_lo: split-bf16 planes of z and

@@ -30,6 +30,9 @@ SIGNATURES = {
     "sgam_frame_outputs": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "sgam_vq_workspace_bytes": (c_sz, [c_i]),
     "sgam_vq_nearest": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "sgam_vq_topk_workspace_bytes": (c_sz, [c_i, c_i]),
+    "sgam_vq_topk_sample": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, ctypes.c_ulonglong, c_i,
+                                  c_p, c_p, c_p, c_p, c_p, c_p]),
     "sgam_vq_norms": (c_i, [c_p, c_p, c_i, c_i, c_p]),
     "sgam_vq_tc_workspace_bytes": (c_sz, [c_i, c_i]),
     "sgam_vq_nearest_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),

@@ -16,7 +16,7 @@ constexpr int ZS = TT + 4, ES = TC + 4;   // padded row strides (floats), keep 1
 
 __global__ void __launch_bounds__(NT)
 vq_distance_argmin_kernel(const float *__restrict__ z, const float *__restrict__ E, int T, int n_e, int D,
-                          unsigned long long *__restrict__ best) {
+                          unsigned long long *__restrict__ best, float *__restrict__ dmat) {
     __shared__ __align__(16) float Zs[BK][ZS];
     __shared__ __align__(16) float Es[BK][ES];
     __shared__ float zz_s[TT], ee_s[TC];
@@ -79,6 +79,7 @@ vq_distance_argmin_kernel(const float *__restrict__ z, const float *__restrict__
             const float d = __fadd_rn(__fsub_rn(__fadd_rn(zz, ee_s[c]), __fmul_rn(2.0f, acc[a][b])), 0.0f);   // quantize.py:285-287 (+0: -0 -> +0)
             const unsigned long long kk = ((unsigned long long)float_orderable(d) << 32) | (unsigned)(c0 + c);
             key = kk < key ? kk : key;
+            if (dmat && t0 + t < T) dmat[(size_t)(t0 + t) * n_e + c0 + c] = d;      // top-k sampling needs every distance
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
@@ -176,6 +177,118 @@ vq_refine_kernel(const float *__restrict__ z, const float *__restrict__ E, const
     for (int k = tid; k < D; k += VQ_TILE) z_q[(size_t)t * D + k] = __ldg(E + (size_t)e * D + k);      // quantize.py:292 / :368
 }
 
+// counter-based uniform in [0,1): splitmix64 of (seed, token, sample)
+__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned t, unsigned s) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)t * 0x100000001B3ull + s + 1);
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (float)(x >> 40) * (1.0f / 16777216.0f);
+}
+
+// quantize.py:344-381 get_multiple_codewords for topk > 1: per token the k nearest codes (ascending distance, first
+// index on ties), p = softmax(-d_topk), S multinomial draws with replacement, tokens whose down-sampled extrapolation
+// mask is 0 pinned to the nearest code.  row0_probs = 1 reproduces the reference, which draws every token from the
+// probabilities of token 0 (quantize.py:358).  One CTA per token; k <= 32.
+constexpr int MAXK = 32;
+__global__ void __launch_bounds__(256)
+vq_topk_sample_kernel(const float *__restrict__ dmat, const float *__restrict__ E, const uint8_t *__restrict__ mask,
+                      long long mask_bstride, int mask_w, int fy, int fx, int lat_w, int tokens_per_image, int n_e, int D, int K, int S,
+                      unsigned long long seed, int row0_probs, int64_t *__restrict__ topk_idx, float *__restrict__ topk_p,
+                      int64_t *__restrict__ idx, float *__restrict__ z_q) {
+    __shared__ unsigned long long red[8];
+    __shared__ unsigned long long chosen[MAXK];
+    __shared__ float prob[MAXK];
+    __shared__ int pick[64];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *row = dmat + (size_t)t * n_e;
+    unsigned long long last = 0;                                   // keys are > 0 for finite d >= -inf ... select strictly increasing keys
+    for (int r = 0; r < K; ++r) {
+        unsigned long long key = ~0ull;
+        for (int c = tid; c < n_e; c += 256) {
+            const unsigned long long kk = ((unsigned long long)float_orderable(row[c]) << 32) | (unsigned)c;
+            if ((r == 0 || kk > last) && kk < key) key = kk;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if (lane == 0) red[warp] = key;
+        __syncthreads();
+        key = red[0];
+        for (int w = 1; w < 8; ++w) key = red[w] < key ? red[w] : key;
+        if (tid == 0) chosen[r] = key;
+        last = key;
+        __syncthreads();
+    }
+    if (tid == 0) {                                                // softmax(-d) over the K candidates (quantize.py:354-355)
+        const float d0 = orderable_float((uint32_t)(chosen[0] >> 32));
+        float sum = 0.f;
+        for (int r = 0; r < K; ++r) { prob[r] = expf(-(orderable_float((uint32_t)(chosen[r] >> 32)) - d0)); sum += prob[r]; }
+        for (int r = 0; r < K; ++r) prob[r] /= sum;
+    }
+    __syncthreads();
+    if (tid < K) {
+        topk_idx[(size_t)t * K + tid] = (int64_t)(chosen[tid] & 0xffffffffull);
+        topk_p[(size_t)t * K + tid] = prob[tid];
+    }
+    // the sampling distribution: own row, or row 0 of the same call (reference behaviour) -- row 0's probabilities are
+    // produced by block 0; to stay single-pass every block recomputes them from row 0's distances when asked to.
+    __shared__ float prob0[MAXK];
+    if (row0_probs && t != 0) {
+        const float *row0 = dmat;                                  // token 0
+        unsigned long long l0 = 0;
+        for (int r = 0; r < K; ++r) {
+            unsigned long long key = ~0ull;
+            for (int c = tid; c < n_e; c += 256) {
+                const unsigned long long kk = ((unsigned long long)float_orderable(row0[c]) << 32) | (unsigned)c;
+                if ((r == 0 || kk > l0) && kk < key) key = kk;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other < key ? other : key;
+            }
+            if (lane == 0) red[warp] = key;
+            __syncthreads();
+            key = red[0];
+            for (int w = 1; w < 8; ++w) key = red[w] < key ? red[w] : key;
+            if (tid == 0) prob0[r] = orderable_float((uint32_t)(key >> 32));
+            l0 = key;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const float d0 = prob0[0];
+            float sum = 0.f;
+            for (int r = 0; r < K; ++r) { prob0[r] = expf(-(prob0[r] - d0)); sum += prob0[r]; }
+            for (int r = 0; r < K; ++r) prob0[r] /= sum;
+        }
+    } else if (tid < K) {
+        prob0[tid] = prob[tid];
+    }
+    __syncthreads();
+    // mask down-sampling: nearest = top-left pixel of each block (quantize.py:345)
+    const int img = t / tokens_per_image, tl = t - img * tokens_per_image;
+    const int ly = tl / lat_w, lx = tl - ly * lat_w;
+    const bool extrapolated = mask ? (mask[(size_t)img * mask_bstride + (size_t)(ly * fy) * mask_w + lx * fx] != 0) : true;
+    if (tid < S) {
+        int r = 0;
+        if (extrapolated) {                                        // pinned tokens keep the nearest code (:364-367)
+            const float u = uniform01(seed, (unsigned)t, (unsigned)tid);
+            float c = 0.f;
+            r = K - 1;
+            for (int k = 0; k < K; ++k) { c += prob0[k]; if (u < c) { r = k; break; } }
+        }
+        pick[tid] = r;
+        idx[(size_t)t * S + tid] = (int64_t)(chosen[r] & 0xffffffffull);
+    }
+    __syncthreads();
+    for (int e = tid; e < S * (D / 4); e += 256) {
+        const int sidx = e / (D / 4), k = e - sidx * (D / 4);
+        const unsigned code = (unsigned)(chosen[pick[sidx]] & 0xffffffffull);
+        reinterpret_cast<float4 *>(z_q + ((size_t)t * S + sidx) * D)[k] = __ldg(reinterpret_cast<const float4 *>(E + (size_t)code * D) + k);
+    }
+}
+
 }  // namespace
 
 int sgam_vq_tilemin_launch(const void *z_hi, const void *z_lo, const void *e_hi, const void *e_lo, const float *zz, const float *ee,
@@ -209,6 +322,28 @@ extern "C" int sgam_vq_nearest_tc(const float *z, const void *z_hi, const void *
     return SGAM_OK;
 }
 
+extern "C" size_t sgam_vq_topk_workspace_bytes(int T, int n_e) { return (size_t)T * n_e * sizeof(float) + (size_t)T * sizeof(unsigned long long); }
+
+extern "C" int sgam_vq_topk_sample(const float *z, const float *codebook, const uint8_t *mask, long long mask_bstride, int mask_w,
+                                   int fy, int fx, int lat_w, int tokens_per_image, int T, int n_e, int D, int topk, int samples,
+                                   unsigned long long seed, int row0_probs, void *workspace, int64_t *topk_idx, float *topk_p,
+                                   int64_t *idx, float *z_q, void *stream) {
+    SGAM_REQUIRE(z && codebook && workspace && topk_idx && topk_p && idx && z_q, "vq_topk_sample: null pointer");
+    SGAM_REQUIRE(T > 0 && D % BK == 0 && n_e % TC == 0, "vq_topk_sample: needs D %% %d == 0 and n_e %% %d == 0", BK, TC);
+    SGAM_REQUIRE(topk >= 1 && topk <= MAXK && topk <= n_e && samples >= 1 && samples <= 64, "vq_topk_sample: topk in [1,%d], samples in [1,64]", MAXK);
+    cudaStream_t s = (cudaStream_t)stream;
+    float *dmat = (float *)workspace;
+    unsigned long long *best = (unsigned long long *)(dmat + (size_t)T * n_e);
+    SGAM_CUDA_OK(cudaMemsetAsync(best, 0xff, (size_t)T * sizeof(unsigned long long), s));
+    dim3 grid(n_e / TC, cdiv(T, TT));
+    vq_distance_argmin_kernel<<<grid, NT, 0, s>>>(z, codebook, T, n_e, D, best, dmat);
+    SGAM_LAUNCH_OK();
+    vq_topk_sample_kernel<<<T, 256, 0, s>>>(dmat, codebook, mask, mask_bstride, mask_w, fy, fx, lat_w, tokens_per_image, n_e, D, topk,
+                                            samples, seed, row0_probs, topk_idx, topk_p, idx, z_q);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
 extern "C" size_t sgam_vq_workspace_bytes(int T) { return (size_t)T * sizeof(unsigned long long); }
 
 extern "C" int sgam_vq_nearest(const float *z, const float *codebook, int T, int n_e, int D, void *best, int64_t *idx,
@@ -219,7 +354,7 @@ extern "C" int sgam_vq_nearest(const float *z, const float *codebook, int T, int
     cudaStream_t s = (cudaStream_t)stream;
     SGAM_CUDA_OK(cudaMemsetAsync(best, 0xff, sgam_vq_workspace_bytes(T), s));
     dim3 grid(n_e / TC, cdiv(T, TT));
-    vq_distance_argmin_kernel<<<grid, NT, 0, s>>>(z, codebook, T, n_e, D, (unsigned long long *)best);
+    vq_distance_argmin_kernel<<<grid, NT, 0, s>>>(z, codebook, T, n_e, D, (unsigned long long *)best, nullptr);
     SGAM_LAUNCH_OK();
     vq_gather_kernel<<<T, 64, 0, s>>>((const unsigned long long *)best, codebook, D, idx, z_q, dmin);
     SGAM_LAUNCH_OK();

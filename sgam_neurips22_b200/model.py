@@ -251,11 +251,18 @@ class VQModel(torch.nn.Module):
         pre_nchw = pre.permute(0, 3, 1, 2)
         if not self.use_vq():
             return pre_nchw
-        if topk is not None and topk != 1:
-            raise NotImplementedError("top-k > 1 sampling (quantize.py:352-367) consumes the global torch RNG 256x "
-                                      "per frame and is not reproducible; the pipeline uses topk=1")
-        if topk is not None and sample_number != 1:
-            raise NotImplementedError("sample_number > 1 only makes sense with topk > 1")
+        if topk is not None and (topk != 1 or sample_number != 1):
+            # quantize.py:352-367 on the device: seeded counter-based sampler (parity with torch's global generator is
+            # distributional, not bitwise); the reference's row-0-probabilities quirk is kept unless switched off
+            B, h, w, D = pre.shape
+            self._sample_calls = getattr(self, "_sample_calls", 0) + 1
+            seed = (torch.initial_seed() * 0x9E3779B1 + self._sample_calls) & 0xFFFFFFFFFFFFFFFF
+            out = ops.vq_topk_sample(pre.view(B * h * w, D), eng.p["quantize.embedding.weight"], int(topk), int(sample_number),
+                                     (h, w), mask=self._mask_u8(extrapolation_mask), seed=seed,
+                                     row0_probs=getattr(self, "sample_row0_probs", True))
+            quants = out["z_q"].view(B, h, w, sample_number, D).permute(0, 3, 4, 1, 2)            # [B,S,D,h,w]
+            idx = out["idx"].view(B, h, w, sample_number).permute(0, 3, 1, 2)
+            return quants, None, (None, None, idx), pre_nchw
         if encoding_indices is not None:
             idx = encoding_indices.reshape(pre.shape[:3]).to(torch.int64)
             z_q = eng.embed_code(idx)

@@ -146,6 +146,30 @@ def vq_nearest(z_tokens, codebook, want_dmin=False, workspace=None):
     return (idx, z_q, dmin) if want_dmin else (idx, z_q)
 
 
+def vq_topk_sample(z_tokens, codebook, topk, samples, lat_hw, mask=None, seed=0, row0_probs=True):
+    """get_multiple_codewords for topk > 1 (quantize.py:344-381).  z_tokens [T,D] = B images of lat_hw = (h, w) tokens;
+    mask [B,1,H,W] / [B,H,W] uint8 or None.  Returns dict(idx [T,S], z_q [T,S,D], topk_idx [T,k], topk_p [T,k])."""
+    lib = _lib.load()
+    _chk(z_tokens, name="z"), _chk(codebook, name="codebook")
+    T, D = z_tokens.shape
+    h, w = lat_hw
+    n_e = codebook.shape[0]
+    dev = z_tokens.device
+    mb, mw, fy, fx = 0, 0, 1, 1
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+        H, W = mask.shape[-2:]
+        mb, mw, fy, fx = H * W, W, H // h, W // w
+    ws = torch.empty(lib.sgam_vq_topk_workspace_bytes(T, n_e) // 4, device=dev)
+    out = dict(idx=torch.empty(T, samples, dtype=torch.int64, device=dev), z_q=torch.empty(T, samples, D, device=dev),
+               topk_idx=torch.empty(T, topk, dtype=torch.int64, device=dev), topk_p=torch.empty(T, topk, device=dev))
+    _lib.check(lib.sgam_vq_topk_sample(z_tokens.data_ptr(), codebook.data_ptr(), _ptr(mask), mb, mw, fy, fx, w, h * w, T, n_e, D,
+                                       topk, samples, seed & 0xFFFFFFFFFFFFFFFF, int(row0_probs), ws.data_ptr(),
+                                       out["topk_idx"].data_ptr(), out["topk_p"].data_ptr(), out["idx"].data_ptr(),
+                                       out["z_q"].data_ptr(), _stream()), "sgam_vq_topk_sample")
+    return out
+
+
 def vq_norms(x):
     """Canonical (sequential fma) squared row norms of x [R,D]."""
     lib = _lib.load()

@@ -43,11 +43,18 @@ class VectorQuantizer2(torch.nn.Module):
         """quantize.py:344-381 for topk=1 (the pipeline's setting, inference_pipeline.py:24,877): the multinomial
         over one candidate draws it, and pinning to the nearest code (:364-367) is the identity, so the result is
         the arg-min for every token.  Returns (z_qs [B,S,D,h,w], None, (None, None, idx [B,S,h,w]))."""
-        if topk != 1 or sample_number != 1:
-            raise NotImplementedError("top-k > 1 sampling consumes the global torch RNG per token and is not "
-                                      "bit-reproducible (SURVEY.md section 8c); only topk=1 is implemented")
-        idx, z_q = self._nearest(z)
         B, D, h, w = z.shape
+        if topk != 1 or sample_number != 1:
+            tokens = z.permute(0, 2, 3, 1).contiguous().view(-1, D)
+            m = None
+            if extrapolation_mask is not None:
+                m = (extrapolation_mask != 0).to(torch.uint8).contiguous()
+            self._calls = getattr(self, "_calls", 0) + 1
+            out = ops.vq_topk_sample(tokens, self.embedding.weight.contiguous(), int(topk), int(sample_number), (h, w), mask=m,
+                                     seed=(torch.initial_seed() * 0x9E3779B1 + self._calls) & 0xFFFFFFFFFFFFFFFF)
+            z_qs = out["z_q"].view(B, h, w, sample_number, D).permute(0, 3, 4, 1, 2).contiguous()
+            return z_qs, None, (None, None, out["idx"].view(B, h, w, sample_number).permute(0, 3, 1, 2))
+        idx, z_q = self._nearest(z)
         return z_q.permute(0, 3, 1, 2).unsqueeze(1), None, (None, None, idx.view(B, 1, h, w))
 
     def get_codebook_entry(self, indices, shape):

@@ -327,3 +327,63 @@ def test_full_step_256_vs_reference(ops, golden, engines, ds):
     ref_d, got_d = golden[f"step256.{ds}.depth_sub"], dm.cpu().numpy()[0, ::4, ::4]
     ok = np.abs(ref_d) < 50
     assert ok.mean() > 0.5 and np.allclose(got_d[ok], ref_d[ok], rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------ stage (ii), top-k sampling
+def test_vq_topk_sampling_matches_reference_distribution(ops, state_dicts):
+    """get_multiple_codewords(topk>1) (quantize.py:344-381): the top-k candidate sets and softmax probabilities must equal
+    the reference expression's; draws come from a seeded device generator, so parity is distributional (chi-square) and
+    the pinning of non-extrapolated tokens is exact."""
+    import torch.nn.functional as F
+    E = state_dicts("google_earth")["quantize.embedding.weight"]
+    rng = np.random.default_rng(5)
+    z = (rng.standard_normal((1, 256, 16, 16)) * 0.9).astype(np.float32)
+    mask = (rng.random((1, 1, 256, 256)) < 0.6)
+    zt = torch.from_numpy(np.ascontiguousarray(z.transpose(0, 2, 3, 1).reshape(-1, 256)))
+    K, S = 10, 64
+    out = ops.vq_topk_sample(zt.cuda(), E.cuda(), K, S, (16, 16), mask=torch.from_numpy(mask).to(torch.uint8).cuda().contiguous(),
+                             seed=1234, row0_probs=True)
+    # reference expression on CPU (quantize.py:348-355)
+    d = torch.sum(zt ** 2, dim=1, keepdim=True) + torch.sum(E ** 2, dim=1) - 2 * torch.einsum('bd,dn->bn', zt, E.permute(1, 0))
+    top = torch.topk(d, K, dim=1, largest=False)
+    probs = F.softmax(-top.values, dim=-1)
+    assert torch.equal(out["topk_idx"].cpu(), top.indices)
+    assert torch.allclose(out["topk_p"].cpu(), probs, atol=2e-4)
+    idx = out["idx"].cpu()                                           # [T, S]
+    mask_ds = F.interpolate(torch.from_numpy(mask).float(), size=(16, 16)).view(-1).bool()      # quantize.py:345
+    assert (idx[~mask_ds] == top.indices[~mask_ds, :1]).all()        # pinned to the nearest code (:364-367)
+    assert torch.equal(out["z_q"].cpu(), E[idx])
+    # every draw is one of the token's k candidates; rank frequencies follow ROW 0's probabilities (the reference's quirk)
+    rank = (idx[:, :, None] == top.indices[:, None, :]).float().argmax(-1)[mask_ds]               # [T', S]
+    assert (idx[:, :, None] == top.indices[:, None, :]).any(-1).all()
+    counts = torch.bincount(rank.reshape(-1), minlength=K).double()
+    expect = probs[0].double() * counts.sum()
+    keep = expect > 5
+    chi2 = (((counts - expect) ** 2 / expect)[keep]).sum().item()
+    assert chi2 < 40, (chi2, counts, expect)                         # dof <= 9: P(chi2 > 40) ~ 1e-5
+    # own-row probabilities when the quirk is switched off; different seeds give different draws; same seed reproduces
+    out2 = ops.vq_topk_sample(zt.cuda(), E.cuda(), K, S, (16, 16), mask=None, seed=1234, row0_probs=False)
+    out3 = ops.vq_topk_sample(zt.cuda(), E.cuda(), K, S, (16, 16), mask=None, seed=1234, row0_probs=False)
+    out4 = ops.vq_topk_sample(zt.cuda(), E.cuda(), K, S, (16, 16), mask=None, seed=99, row0_probs=False)
+    assert torch.equal(out2["idx"], out3["idx"]) and not torch.equal(out2["idx"], out4["idx"])
+    rank2 = (out2["idx"].cpu()[:, :, None] == top.indices[:, None, :]).float().argmax(-1)
+    emp = torch.stack([(rank2 == k).float().mean(1) for k in range(K)], 1)                         # [T, K] empirical
+    assert (emp - probs).abs().mean().item() < 0.03
+
+
+def test_vqmodel_topk_sampling_api(state_dicts):
+    """VQModel.forward(topk>1, sample_number>1): the reference's return structure (model.py:152-167)."""
+    from sgam_neurips22_b200 import synthetic
+    from sgam_neurips22_b200.model import VQModel
+    torch.manual_seed(3)
+    model = synthetic.randomize_weights(VQModel(**synthetic.model_kwargs("google_earth")), seed=0).to("cuda:0").eval()
+    x = torch.rand(1, 4, 64, 64).cuda() * 2 - 1
+    m = (torch.rand(1, 1, 64, 64) < 0.5).cuda()
+    decs, diff, pre, quants = model(x, topk=5, extrapolation_mask=m, sample_number=3, get_pre_quantized_feature=True,
+                                    get_quantized_feature=True)
+    assert len(decs) == 3 and tuple(decs[0].shape) == (1, 1, 4, 64, 64) and diff is None
+    assert tuple(quants.shape) == (1, 3, 256, 4, 4) and tuple(pre.shape) == (1, 256, 4, 4)
+    nearest = model(x, topk=1, extrapolation_mask=m, get_quantized_feature=True)[2]
+    pinned = ~m[:, :, ::16, ::16].expand(1, 256, 4, 4)
+    for s in range(3):
+        assert torch.equal(quants[:, s][pinned], nearest[:, 0][pinned])
