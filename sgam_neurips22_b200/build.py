@@ -23,6 +23,7 @@ SOURCES = {
     "vq.cu": ["--fmad=false"],
     "net_simt.cu": [],
     "net_tc.cu": [],
+    "net_tc2.cu": [],
     "net_tc_prep.cu": [],
 }
 
