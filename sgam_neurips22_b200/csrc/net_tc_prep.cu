@@ -8,26 +8,27 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------ producers of split bf16
-// x fp32 [B, H, W, C] -> hi / lo bf16 [B, H<<up, W<<up, C] (nearest x2 up-sampling fused when up = 1)
+// x fp32 [B, H, W, C] -> hi / lo bf16 [B, H<<up, W<<up, C] (nearest x2 up-sampling fused when up = 1).
+// 8 channels per thread: two 16-byte loads, one 16-byte store per plane.
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
-                  long long total_q, int H, int W, int CQ, int up) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_q; e += (long long)gridDim.x * blockDim.x) {
+                  long long total_o, int H, int W, int CO, int up) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_o; e += (long long)gridDim.x * blockDim.x) {
         long long src = e;
         if (up) {
-            const int cq = (int)(e % CQ);
-            long long pix = e / CQ;
+            const int co = (int)(e % CO);
+            long long pix = e / CO;
             const int Wo = W * 2, Ho = H * 2;
             const int ox = (int)(pix % Wo); pix /= Wo;
             const int oy = (int)(pix % Ho); const long long b = pix / Ho;
-            src = (((b * H + (oy >> 1)) * W + (ox >> 1)) * CQ) + cq;
+            src = (((b * H + (oy >> 1)) * W + (ox >> 1)) * CO) + co;
         }
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + src);
-        uint32_t h[2], l[2];
-        split2(v.x, v.y, h[0], l[0]);
-        split2(v.z, v.w, h[1], l[1]);
-        reinterpret_cast<uint2 *>(hi)[e] = make_uint2(h[0], h[1]);
-        reinterpret_cast<uint2 *>(lo)[e] = make_uint2(l[0], l[1]);
+        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * src), v1 = __ldg(reinterpret_cast<const float4 *>(x) + 2 * src + 1);
+        uint32_t h[4], l[4];
+        split2(v0.x, v0.y, h[0], l[0]); split2(v0.z, v0.w, h[1], l[1]);
+        split2(v1.x, v1.y, h[2], l[2]); split2(v1.z, v1.w, h[3], l[3]);
+        reinterpret_cast<uint4 *>(hi)[e] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4 *>(lo)[e] = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
@@ -53,46 +54,57 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
         rstd_s[tid] = (float)(1.0 / sqrt(var + 1e-6));
     }
     __syncthreads();
-    const int CQ = C / 4, cpg = C / 32;
-    const long long total = HW * CQ;
+    const int CO = C / 8, cpg = C / 32;                 // 8 channels per thread (cpg >= 4: at most two groups)
+    const long long total = HW * CO;
     const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)b * HW * C);
-    uint2 *dh = reinterpret_cast<uint2 *>(hi + (size_t)b * HW * C), *dl = reinterpret_cast<uint2 *>(lo + (size_t)b * HW * C);
+    uint4 *dh = reinterpret_cast<uint4 *>(hi + (size_t)b * HW * C), *dl = reinterpret_cast<uint4 *>(lo + (size_t)b * HW * C);
     for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(e % CQ), c = cq * 4, g = c / cpg;
-        const float mu = mean_s[g], rs = rstd_s[g];
-        const float4 v = __ldg(src + e), ga = __ldg(reinterpret_cast<const float4 *>(gamma + c)),
-                     be = __ldg(reinterpret_cast<const float4 *>(beta + c));
-        float o[4] = {(v.x - mu) * rs * ga.x + be.x, (v.y - mu) * rs * ga.y + be.y,
-                      (v.z - mu) * rs * ga.z + be.z, (v.w - mu) * rs * ga.w + be.w};
+        const int c = (int)(e % CO) * 8, g0 = c / cpg, g1 = (c + 4) / cpg;
+        const float mu0 = mean_s[g0], rs0 = rstd_s[g0], mu1 = mean_s[g1], rs1 = rstd_s[g1];
+        const float4 v0 = __ldg(src + 2 * e), v1 = __ldg(src + 2 * e + 1);
+        const float4 ga0 = __ldg(reinterpret_cast<const float4 *>(gamma + c)), ga1 = __ldg(reinterpret_cast<const float4 *>(gamma + c + 4));
+        const float4 be0 = __ldg(reinterpret_cast<const float4 *>(beta + c)), be1 = __ldg(reinterpret_cast<const float4 *>(beta + c + 4));
+        float o[8] = {(v0.x - mu0) * rs0 * ga0.x + be0.x, (v0.y - mu0) * rs0 * ga0.y + be0.y,
+                      (v0.z - mu0) * rs0 * ga0.z + be0.z, (v0.w - mu0) * rs0 * ga0.w + be0.w,
+                      (v1.x - mu1) * rs1 * ga1.x + be1.x, (v1.y - mu1) * rs1 * ga1.y + be1.y,
+                      (v1.z - mu1) * rs1 * ga1.z + be1.z, (v1.w - mu1) * rs1 * ga1.w + be1.w};
         if (swish) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = o[k] / (1.0f + expf(-o[k]));
+            for (int k = 0; k < 8; ++k) o[k] = o[k] / (1.0f + expf(-o[k]));
         }
-        uint32_t h[2], l[2];
-        split2(o[0], o[1], h[0], l[0]);
-        split2(o[2], o[3], h[1], l[1]);
-        dh[e] = make_uint2(h[0], h[1]);
-        dl[e] = make_uint2(l[0], l[1]);
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split2(o[2 * k], o[2 * k + 1], h[k], l[k]);
+        dh[e] = make_uint4(h[0], h[1], h[2], h[3]);
+        dl[e] = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
-// row softmax of fp32 scores -> split-bf16 probabilities (model.py:181); cols % 2 == 0.
-// VPT > 0: the row (cols <= 256*2*VPT) is read ONCE into registers (8 B in, 8 B out per pair); VPT = 0: three-pass fallback.
+// row softmax of fp32 scores -> split-bf16 probabilities (model.py:181); cols % 8 == 0.
+// VPT > 0: the row (cols <= 2048*VPT) is read ONCE into registers, 8 consecutive elements per thread per chunk
+// (two 16-byte loads, one 16-byte store per plane); VPT = 0: three-pass fallback for very long rows.
 template <int VPT>
 __global__ void __launch_bounds__(256)
 softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cols) {
     __shared__ float sh[8];
     const float *row = x + (size_t)blockIdx.x * cols;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = cols / 2;
-    uint32_t *dh = reinterpret_cast<uint32_t *>(hi + (size_t)blockIdx.x * cols), *dl = reinterpret_cast<uint32_t *>(lo + (size_t)blockIdx.x * cols);
-    float2 v[VPT > 0 ? VPT : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = cols / 8;
+    uint4 *dh = reinterpret_cast<uint4 *>(hi + (size_t)blockIdx.x * cols), *dl = reinterpret_cast<uint4 *>(lo + (size_t)blockIdx.x * cols);
+    float v[VPT > 0 ? VPT : 1][8];
     float mx = -INFINITY;
     if (VPT > 0) {
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
             const int c = threadIdx.x + i * 256;
-            v[i] = (c < half) ? __ldg(reinterpret_cast<const float2 *>(row) + c) : make_float2(-INFINITY, -INFINITY);
-            mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
+            if (c < oct) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(row) + 2 * c), b4 = __ldg(reinterpret_cast<const float4 *>(row) + 2 * c + 1);
+                v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b4.x; v[i][5] = b4.y; v[i][6] = b4.z; v[i][7] = b4.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[i][k] = -INFINITY;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx = fmaxf(mx, v[i][k]);
         }
     } else {
         for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, row[c]);
@@ -107,7 +119,9 @@ softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi
     float sum = 0.f;
     if (VPT > 0) {
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) { v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx); sum += v[i].x + v[i].y; }
+        for (int i = 0; i < VPT; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { v[i][k] = expf(v[i][k] - mx); sum += v[i][k]; }
     } else {
         for (int c = threadIdx.x; c < cols; c += 256) sum += expf(row[c] - mx);
     }
@@ -122,14 +136,22 @@ softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
             const int c = threadIdx.x + i * 256;
-            if (c < half) { uint32_t h, l; split2(v[i].x * inv, v[i].y * inv, h, l); dh[c] = h; dl[c] = l; }
+            if (c < oct) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) split2(v[i][2 * k] * inv, v[i][2 * k + 1] * inv, h[k], l[k]);
+                dh[c] = make_uint4(h[0], h[1], h[2], h[3]);
+                dl[c] = make_uint4(l[0], l[1], l[2], l[3]);
+            }
         }
     } else {
-        for (int c = threadIdx.x; c < half; c += 256) {
-            const float2 t = *reinterpret_cast<const float2 *>(row + 2 * c);
-            uint32_t h, l;
-            split2(expf(t.x - mx) * inv, expf(t.y - mx) * inv, h, l);
-            dh[c] = h; dl[c] = l;
+        for (int c = threadIdx.x; c < oct; c += 256) {
+            const float4 a = *reinterpret_cast<const float4 *>(row + 8 * c), b4 = *reinterpret_cast<const float4 *>(row + 8 * c + 4);
+            uint32_t h[4], l[4];
+            split2(expf(a.x - mx) * inv, expf(a.y - mx) * inv, h[0], l[0]); split2(expf(a.z - mx) * inv, expf(a.w - mx) * inv, h[1], l[1]);
+            split2(expf(b4.x - mx) * inv, expf(b4.y - mx) * inv, h[2], l[2]); split2(expf(b4.z - mx) * inv, expf(b4.w - mx) * inv, h[3], l[3]);
+            dh[c] = make_uint4(h[0], h[1], h[2], h[3]);
+            dl[c] = make_uint4(l[0], l[1], l[2], l[3]);
         }
     }
 }
@@ -200,10 +222,10 @@ extern "C" int sgam_stem_conv_split(const float *x, const uint8_t *mask, const f
 }
 
 extern "C" int sgam_split_bf16(const float *x, void *hi, void *lo, int B, int H, int W, int C, int upsample, void *stream) {
-    SGAM_REQUIRE(x && hi && lo && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "split_bf16: bad arguments");
-    const long long total_q = (long long)B * (H << upsample) * (W << upsample) * (C / 4);
-    const unsigned blocks = (unsigned)min((long long)148 * 16, (total_q + 255) / 256);
-    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, total_q, H, W, C / 4, upsample);
+    SGAM_REQUIRE(x && hi && lo && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "split_bf16: C must be a multiple of 8");
+    const long long total_o = (long long)B * (H << upsample) * (W << upsample) * (C / 8);
+    const unsigned blocks = (unsigned)min((long long)148 * 16, (total_o + 255) / 256);
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, total_o, H, W, C / 8, upsample);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
@@ -215,7 +237,7 @@ extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const fl
     cudaStream_t s = (cudaStream_t)stream;
     int rc = sgam_gn_stats_launch(x, partial, B, HW, C, s);
     if (rc) return rc;
-    const long long total = HW * (C / 4);
+    const long long total = HW * (C / 8);
     const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
     gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
                                                           sgam_gn_splits(HW), swish);
@@ -240,7 +262,7 @@ extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, co
     float *meanrstd = gn_partial + (long long)B * tiles * 64;
     gn_finalize_kernel<<<B, 256, 0, s>>>(gn_partial, meanrstd, tiles, (double)HW * (C / 32));
     SGAM_LAUNCH_OK();
-    const long long total = HW * (C / 4);
+    const long long total = HW * (C / 8);
     const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
     gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
     SGAM_LAUNCH_OK();
@@ -248,13 +270,12 @@ extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, co
 }
 
 extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long rows, int cols, void *stream) {
-    SGAM_REQUIRE(x && hi && lo && rows > 0 && cols > 0 && cols % 2 == 0, "softmax_split: bad arguments");
+    SGAM_REQUIRE(x && hi && lo && rows > 0 && cols > 0 && cols % 8 == 0, "softmax_split: cols must be a multiple of 8");
     cudaStream_t s = (cudaStream_t)stream;
     __nv_bfloat16 *h = (__nv_bfloat16 *)hi, *l = (__nv_bfloat16 *)lo;
-    if (cols <= 512) softmax_split_kernel<1><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else if (cols <= 2048) softmax_split_kernel<4><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else if (cols <= 4096) softmax_split_kernel<8><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else if (cols <= 16384) softmax_split_kernel<32><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    if (cols <= 2048) softmax_split_kernel<1><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else if (cols <= 4096) softmax_split_kernel<2><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
+    else if (cols <= 16384) softmax_split_kernel<8><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
     else softmax_split_kernel<0><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
