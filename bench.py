@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="independent trajectories per GPU (BASELINE.json configs[3]: 64 over 8 GPUs)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     ap.add_argument("--dump-gemm", default=None, help="write the per-launch table of the tensor-core GEMMs of one step to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -213,6 +215,16 @@ def main():
     step_resident()
     torch.cuda.synchronize()
     launches_per_step = int(lib.sgam_launch_count() - c0)
+
+    if args.profile_step:
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
 
     run_step = step_resident
     graph = None
@@ -371,7 +383,8 @@ def main():
             seed = (rng.integers(0, 256, (256, 256, 3)).astype(np.uint8),
                     (lo + (hi - lo) * (0.5 + 0.3 * np.sin(3 * xx) * np.cos(2 * yy))).astype(np.float32))
             dim = (5, 6) if ds == "clevr-infinite" else (30, 1)
-            pipe = InfiniteSceneGeneration(model, ds, seed_frame=seed, output_dim=dim)
+            rgbd = ds == "google_earth"          # BASELINE.json configs[2]: the GoogleEarth loop runs with use_rgbd_integration=True
+            pipe = InfiniteSceneGeneration(model, ds, seed_frame=seed, output_dim=dim, use_rgbd_integration=rgbd)
             n_loop, skip = dim[0] * dim[1] - 1, 5
             for i in range(n_loop):
                 if i == skip:
@@ -384,7 +397,8 @@ def main():
             scene_loop = {"value": (n_loop - skip) / dt, "unit": UNIT, "ms_per_frame": 1000.0 * dt / (n_loop - skip), "frames": n_loop - skip,
                           "note": "InfiniteSceneGeneration.one_step_prediction, one trajectory, frames generated sequentially from the "
                                   "device-resident frame store (source selection, pose math, splat, forward, uint8/depth conversion), "
-                                  "no disk writes, wall clock on rank 0"}
+                                  "no disk writes, wall clock on rank 0" +
+                                  ("; use_rgbd_integration=True: device TSDF integration + ray-cast target depth + inverse warp" if rgbd else "")}
         finally:
             os.chdir(cwd)
 

@@ -7,6 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "csrc", "oracle.c")
+_SRCS = [_SRC, os.path.join(_HERE, "csrc", "tsdf_oracle.c")]
 _OUT_DIR = os.path.join(_HERE, "_build")
 _SO = os.path.join(_OUT_DIR, "liboracle.so")
 _lib = None
@@ -17,9 +18,9 @@ DATASET_ID = {"clevr-infinite": 0, "google_earth": 1}
 def build(force=False):
     """gcc recipe for the C restatement (also run by __graft_entry__.build())."""
     os.makedirs(_OUT_DIR, exist_ok=True)
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in _SRCS):
         cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off", "-mfma", "-fopenmp",
-               "-o", _SO, _SRC, "-lm"]
+               "-o", _SO, *_SRCS, "-lm"]
         subprocess.check_call(cmd)
     return _SO
 
@@ -114,3 +115,57 @@ def unproject_world(depth, Kinv, Rt_inv):
     out = np.empty((H * W, 3), np.float64)
     lib().oracle_unproject_world(_p(depth), _p(Kinv), _p(Rt_inv), H, W, _p(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- TSDF (parity unpinned)
+class TsdfGrid(ctypes.Structure):
+    _fields_ = [("ox", ctypes.c_int), ("oy", ctypes.c_int), ("oz", ctypes.c_int),
+                ("nx", ctypes.c_int), ("ny", ctypes.c_int), ("nz", ctypes.c_int),
+                ("voxel_length", ctypes.c_float), ("sdf_trunc", ctypes.c_float)]
+
+
+class TsdfVolume:
+    """Host twin of sgam_neurips22_b200.tsdf.TSDFVolume on oracle/csrc/tsdf_oracle.c (same layout, same arguments)."""
+
+    def __init__(self, voxel_length, sdf_trunc, origin_units, dims_units, with_color=True):
+        self.grid = TsdfGrid(*[int(v) for v in origin_units], *[int(v) for v in dims_units], float(voxel_length), float(sdf_trunc))
+        n = int(np.prod(dims_units))
+        self.stamp = np.zeros(n, np.uint32)
+        self.vol = np.zeros((n, 4096, 2), np.float32)
+        self.color = np.zeros((n, 4096, 3), np.float32) if with_color else None
+        self.frame = 0
+
+    def integrate(self, depth, rgb, K4, world2cam, stride=4, depth_trunc=20.0):
+        """depth [H,W] fp32, rgb [H,W,3] fp32 in [-1,1] or None, K4 = (fx,fy,cx,cy), world2cam 4x4 float64."""
+        depth = _f(depth)
+        H, W = depth.shape
+        rgb = _f(rgb) if (rgb is not None and self.color is not None) else None
+        w2c = np.asarray(world2cam, np.float64)
+        c2w = np.ascontiguousarray(np.linalg.inv(w2c)[:3], np.float64)
+        w2c32 = np.ascontiguousarray(w2c[:3], np.float32)
+        K = np.ascontiguousarray(K4, np.float64)
+        self.frame += 1
+        L = lib()
+        L.oracle_tsdf_touch(_p(depth), H, W, _p(c2w), _p(K), int(stride), ctypes.c_float(depth_trunc),
+                            ctypes.byref(self.grid), _p(self.stamp), ctypes.c_uint32(self.frame))
+        L.oracle_tsdf_integrate(_p(depth), _p(rgb), H, W, _p(w2c32), _p(K), ctypes.c_float(depth_trunc),
+                                ctypes.byref(self.grid), _p(self.stamp), ctypes.c_uint32(self.frame), _p(self.vol),
+                                _p(self.color) if rgb is not None else None)
+
+    def render_depth(self, K4, world2cam, H, W, pixel_center=0.5, z_near=0.05, z_far=20.0, step_vox=0.5):
+        c2w32 = np.ascontiguousarray(np.linalg.inv(np.asarray(world2cam, np.float64))[:3], np.float32)
+        K = np.ascontiguousarray(K4, np.float64)
+        out = np.empty((H, W), np.float32)
+        lib().oracle_tsdf_raycast(ctypes.byref(self.grid), _p(self.stamp), _p(self.vol), _p(c2w32), _p(K),
+                                  ctypes.c_float(pixel_center), H, W, ctypes.c_float(z_near), ctypes.c_float(z_far),
+                                  ctypes.c_float(step_vox), _p(out))
+        return out
+
+    def extract_point_cloud(self):
+        L = lib()
+        L.oracle_tsdf_extract.restype = ctypes.c_long
+        col = _p(self.color) if self.color is not None else None
+        n = L.oracle_tsdf_extract(ctypes.byref(self.grid), _p(self.stamp), _p(self.vol), col, None, None)
+        xyz, rgb = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        L.oracle_tsdf_extract(ctypes.byref(self.grid), _p(self.stamp), _p(self.vol), col, _p(xyz), _p(rgb))
+        return xyz, rgb

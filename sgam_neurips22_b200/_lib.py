@@ -14,6 +14,7 @@ c_i = ctypes.c_int
 c_ll = ctypes.c_longlong
 c_f = ctypes.c_float
 c_sz = ctypes.c_size_t
+c_u32 = ctypes.c_uint32
 
 # name -> (restype, argtypes); mirrors include/sgam_b200.h one to one (tests/test_abi.py checks the header)
 SIGNATURES = {
@@ -52,6 +53,12 @@ SIGNATURES = {
     "sgam_tc_gn_partial_floats": (c_ll, [c_i, c_i, c_i]),
     "sgam_groupnorm_split_fused": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sgam_gemm_nt_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p]),
+    "sgam_tsdf_volume_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
+    "sgam_tsdf_integrate": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f,
+                                  c_p, c_u32, c_p, c_p, c_p]),
+    "sgam_tsdf_raycast": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_f, c_i, c_i, c_f, c_f, c_f,
+                                c_p, c_p]),
+    "sgam_tsdf_extract": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p]),
 }
 
 _lib = None

@@ -21,6 +21,7 @@ SOURCES = {
     "abi.cu": [],
     "splat.cu": ["--fmad=false"],
     "vq.cu": ["--fmad=false"],
+    "tsdf.cu": ["--fmad=false"],
     "net_simt.cu": [],
     "net_tc.cu": [],
     "net_tc2.cu": [],

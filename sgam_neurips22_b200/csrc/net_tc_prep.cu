@@ -70,7 +70,7 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
                       (v1.z - mu1) * rs1 * ga1.z + be1.z, (v1.w - mu1) * rs1 * ga1.w + be1.w};
         if (swish) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = o[k] / (1.0f + expf(-o[k]));
+            for (int k = 0; k < 8; ++k) o[k] = __fdividef(o[k], 1.0f + __expf(-o[k]));   // <= 3 ulp; keeps the kernel HBM-bound
         }
         uint32_t h[4], l[4];
 #pragma unroll

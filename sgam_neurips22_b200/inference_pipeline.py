@@ -11,9 +11,10 @@ unchanged.  What is re-designed:
   * the per-source Python z-test loop of `inverse_warping` (:725-737) is one kernel;
   * no matplotlib (`plt.show()` per frame, :903-904), no tqdm prints in the step.
 
-Open3D (TSDF fusion + mesh depth render for use_rgbd_integration=True, :745-838) is a third-party C++ wheel that is
-not in the target image: `tsdf_depth_fn` lets the caller supply the integrated target depth; without it and without
-open3d, `use_rgbd_integration=True` raises.
+use_rgbd_integration=True (:745-838; the README default) runs on a device-resident TSDF volume (tsdf.py / csrc/tsdf.cu):
+the selected source frames are integrated with Open3D 0.15.2's ScalableTSDFVolume arithmetic and the target depth is
+ray-cast from the volume -- no Open3D, no mesh extraction, no off-screen renderer, no host round trip.  `tsdf_depth_fn`
+lets the caller substitute any other integrated-depth source (e.g. the real Open3D where it is installed).
 """
 import os
 import shutil
@@ -24,6 +25,12 @@ import torch
 
 from . import ops
 from .model import VQModel
+from .tsdf import TSDFVolume, frustum_box
+
+# (voxel_length, sdf_trunc) of the reference's ScalableTSDFVolume (:119-131) and the far end of each dataset's depth
+# code (model.py:211-226), which bounds the dense grid
+TSDF_PARAMS = {"clevr-infinite": (0.05, 0.5), "google_earth": (0.01, 0.03)}
+DEPTH_FAR = {"clevr-infinite": 16.0, "google_earth": 14.765625 - 10.0}
 
 
 def _ray_to_z(depth, K):
@@ -124,14 +131,7 @@ class InfiniteSceneGeneration:
 
         self.volume = None
         if self.use_rgbd_integration and tsdf_depth_fn is None:
-            try:
-                import open3d as o3d                                        # noqa: F401
-            except Exception as e:                                         # noqa: BLE001
-                raise NotImplementedError(
-                    "use_rgbd_integration=True needs Open3D's ScalableTSDFVolume + OffscreenRenderer "
-                    "(inference_pipeline.py:119-133, 745-838), which is not installed; pass tsdf_depth_fn=... to "
-                    "supply the integrated target depth") from e
-            self._init_open3d()
+            self._init_volume()
 
     # ------------------------------------------------------------------------------------ seed / files
     def _stage_seed(self, template_root, seed_frame):
@@ -275,10 +275,10 @@ class InfiniteSceneGeneration:
                  "dst_img": torch.zeros(1, H, W, 3), "dst_depth": torch.zeros(1, H, W),
                  "src_imgs": src_imgs, "src_depths": src_depths}
         if self.use_rgbd_integration:
-            tgt_depth = self.rgbd_integration(src_nodes, T_tgt)             # [H,W] fp32 on device
             first = tuple(self._ordered_grid_coords[0])                     # the seed's second ray->z conversion happens
             dm_iw = torch.stack([self._seed_depth_single if tuple(n["grid_coord"]) == first else self._frames[tuple(n["grid_coord"])][1]
                                  for n in src_nodes])[None]                 # after the inverse warp in the reference (:570-590)
+            tgt_depth = self.rgbd_integration(src_nodes, T_tgt, src_depths=dm_iw[0])   # [H,W] fp32 on device
             warped = self.inverse_warping(src_imgs.permute(0, 1, 4, 2, 3), dm_iw, tgt_depth[None],
                                           batch["Ks"], f32(self.K)[None], f32(np.stack(T_tgt2srcs))[None], as_numpy=False)
             batch["warped_tgt_features"] = warped[None]
@@ -303,40 +303,35 @@ class InfiniteSceneGeneration:
                                Kinv_tgt.to(dev).contiguous(), proj.to(dev).contiguous(), channels_last=channels_last)
         return out[0].cpu().numpy() if as_numpy else out[0]
 
-    def rgbd_integration(self, src_nodes, T_tgt):
-        """Integrated target depth [H,W] on the device (:745-838)."""
+    def _init_volume(self):
+        """:119-131: the TSDF volume, as a dense device grid over the box the trajectory's view frusta can reach."""
+        H, W = self.image_resolution
+        vox, trunc = TSDF_PARAMS[self.data]
+        self._z_far = 1.1 * DEPTH_FAR[self.data]
+        poses = []
+        for row in self.transform_grid:
+            for node in row:
+                T = np.eye(4)
+                T[:3, :3], T[:3, 3] = node["R"], node["t"]
+                poses.append(T)
+        lo, hi = frustum_box(self.K, poses, H, W, self._z_far, pad=trunc + 16 * vox)
+        self.volume = TSDFVolume(vox, trunc, lo, hi, device=self.device, with_color=True)
+
+    def rgbd_integration(self, src_nodes, T_tgt, src_depths=None):
+        """Integrated target depth [H,W] on the device (:745-838): integrate the selected source frames into the
+        volume (again at every step they are selected, like the reference), then render the target view's depth."""
         if self.tsdf_depth_fn is not None:
             d = self.tsdf_depth_fn(self, src_nodes, T_tgt)
             return torch.as_tensor(d).to(self.device, torch.float32).contiguous()
-        return self._open3d_depth(src_nodes, T_tgt)
-
-    # Open3D glue is kept minimal and is exercised only where the wheel exists.
-    def _init_open3d(self):   # pragma: no cover
-        import open3d as o3d
-        vox, trunc = (0.05, 0.5) if self.data == "clevr-infinite" else (0.01, 0.03)     # :119-131
-        self.volume = o3d.pipelines.integration.ScalableTSDFVolume(
-            voxel_length=vox, sdf_trunc=trunc, color_type=o3d.pipelines.integration.TSDFVolumeColorType.RGB8)
-
-    def _open3d_depth(self, src_nodes, T_tgt):   # pragma: no cover
-        import open3d as o3d
         H, W = self.image_resolution
-        intr = o3d.camera.PinholeCameraIntrinsic(W, H, self.K[0][0], self.K[1][1], self.K[0][2], self.K[1][2])
-        for n in src_nodes:
+        for i, n in enumerate(src_nodes):
             rgb, depth = self._frames[tuple(n["grid_coord"])]
-            rgb_u8 = ((rgb.cpu().numpy().astype(np.float64) + 1.0) * 127.5 + 0.5).astype(np.uint8)
-            rgbd = o3d.geometry.RGBDImage.create_from_color_and_depth(
-                o3d.geometry.Image(np.ascontiguousarray(rgb_u8)), o3d.geometry.Image(depth.cpu().numpy()),
-                depth_scale=1.0, depth_trunc=1000.0, convert_rgb_to_intensity=False)
-            Rt = np.eye(4)
-            Rt[:3, :3], Rt[:3, 3] = n["R"], n["t"]
-            self.volume.integrate(rgbd, intr, Rt)
-        mesh = self.volume.extract_triangle_mesh()
-        renderer = o3d.visualization.rendering.OffscreenRenderer(W, H)
-        renderer.scene.add_geometry("mesh", mesh, o3d.visualization.rendering.MaterialRecord())
-        renderer.setup_camera(intr, T_tgt)
-        d = np.asarray(renderer.render_to_depth_image(z_in_view_space=True))
-        d[np.isinf(d)] = 0
-        return torch.from_numpy(d.astype(np.float32)).to(self.device)
+            if src_depths is not None:
+                depth = src_depths[i]
+            T_src = np.eye(4)
+            T_src[:3, :3], T_src[:3, 3] = n["R"], n["t"]
+            self.volume.integrate(depth.contiguous(), rgb, self.K, T_src, depth_trunc=20.0)      # :771-777
+        return self.volume.render_depth(self.K, T_tgt, H, W, z_far=self._z_far)                  # :786-827
 
     # ------------------------------------------------------------------------------------ the step
     @torch.no_grad()
@@ -391,6 +386,11 @@ class InfiniteSceneGeneration:
         merged = str(self.grid_transform_path / "merged_pcds.ply")
         write_ply(merged, xyz, rgb)
         print(f"Merged per-view point cloud is saved at {merged}")
+        if self.use_rgbd_integration and isinstance(self.volume, TSDFVolume):                 # :446-450
+            pts, cols = self.volume.extract_point_cloud()
+            path = str(self.grid_transform_path / "rgbd_integrated_mesh.ply")
+            write_ply(path, pts.cpu().numpy(), cols.cpu().numpy())
+            print(f"RGB-D integrated point cloud is saved at {path}")
 
     # ------------------------------------------------------------------------------------ final map
     def prepare_pcd(self, depth, color, K, Rt):
