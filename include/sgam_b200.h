@@ -231,11 +231,12 @@ int sgam_gemm_nt_tc(const void *a_hi, const void *a_lo, const void *b_hi, const 
 size_t sgam_tsdf_volume_bytes(int nx, int ny, int nz, int with_color);
 /* one RGB-D frame: depth [H,W] (>= depth_trunc or <= 0 ignored), rgb [H,W,3] fp32 in [-1,1] (uint8 lattice) or NULL;
  * opens the units within sdf_trunc of every `stride`-th depth sample (host_cam2world, fp64) and integrates them
- * (host_world2cam, fp32).  frame must be non-zero and distinct per call. */
+ * (host_world2cam, fp32).  frame must be non-zero and distinct per call; work [1 + nx*ny*nz] i32 scratch (the
+ * frame's list of opened units). */
 int sgam_tsdf_integrate(const float *depth, const float *rgb, int H, int W, const double *host_cam2world,
                         const float *host_world2cam, const double *host_K, int stride, float depth_trunc,
                         int ox, int oy, int oz, int nx, int ny, int nz, float voxel_length, float sdf_trunc,
-                        uint32_t *stamp, uint32_t frame, float *vol, float *color, void *stream);
+                        uint32_t *stamp, uint32_t frame, int *work, float *vol, float *color, void *stream);
 /* view-space z of the first + -> - crossing along the ray of pixel (u + pixel_center, v + pixel_center); 0 = no surface.
  * Samples every step_vox voxel lengths of z in [z_near, z_far], skipping never-opened units.  out [H,W]. */
 int sgam_tsdf_raycast(const uint32_t *stamp, const float *vol, int ox, int oy, int oz, int nx, int ny, int nz,

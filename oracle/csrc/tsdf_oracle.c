@@ -136,7 +136,8 @@ static inline void fetch(const tsdf_grid *g, const uint32_t *stamp, const float 
  * ((u + pc - cx)/fx, (v + pc - cy)/fy, 1) so the ray parameter IS the view-space z the reference asks for
  * (render_to_depth_image(z_in_view_space=True)); no hit -> 0 (:827 inf -> 0).
  * Samples every `step_vox` voxel lengths of z in [z_near, z_far]; inside a never-opened unit the ray jumps to the
- * unit's exit.  A sample is valid when all 8 trilinear corners have weight > 0. */
+ * unit's exit; through observed free space it takes coarse steps.  A sample is valid when all 8 trilinear corners have
+ * weight > 0. */
 void oracle_tsdf_raycast(const tsdf_grid *g, const uint32_t *stamp, const float *vol, const float *cam2world,
                          const double *K, float pixel_center, int H, int W, float z_near, float z_far, float step_vox,
                          float *out) {
@@ -149,7 +150,10 @@ void oracle_tsdf_raycast(const tsdf_grid *g, const uint32_t *stamp, const float 
             dw[r] = (cam2world[4 * r] * dc[0] + cam2world[4 * r + 1] * dc[1] + cam2world[4 * r + 2] * dc[2]) * inv_vl;
             ow[r] = cam2world[4 * r + 3] * inv_vl - 0.5f;          /* voxel coordinates: voxel i is centred at i */
         }
-        float t = z_near, t_prev = 0.0f, f_prev = 0.0f, hit = 0.0f;
+        /* observed free space (tsdf clamped at +1) is crossed in coarse steps of 0.8 sdf_trunc of ray length; a sign
+         * change found by a coarse step is re-walked finely */
+        const float coarse = 0.8f * g->sdf_trunc / sqrtf(dc[0] * dc[0] + dc[1] * dc[1] + 1.0f);
+        float t = z_near, t_prev = 0.0f, f_prev = 0.0f, hit = 0.0f, fine_until = -1.0f;
         int prev_valid = 0, guard = 0;
         while (t <= z_far && guard++ < 100000) {
             const float p[3] = {ow[0] + t * dw[0], ow[1] + t * dw[1], ow[2] + t * dw[2]};
@@ -173,20 +177,21 @@ void oracle_tsdf_raycast(const tsdf_grid *g, const uint32_t *stamp, const float 
             const float a[3] = {p[0] - fl[0], p[1] - fl[1], p[2] - fl[2]};
             float f = 0.0f;
             int valid = 1;
-            for (int c = 0; c < 8 && valid; ++c) {
+            for (int c = 0; c < 8; ++c) {
                 const int ix = c & 1, iy = (c >> 1) & 1, iz = c >> 2;
                 float fv, wv;
                 fetch(g, stamp, vol, b[0] + ix, b[1] + iy, b[2] + iz, &fv, &wv);
-                if (!(wv > 0.0f)) { valid = 0; break; }
+                if (!(wv > 0.0f)) valid = 0;
                 const float wx = ix ? a[0] : 1.0f - a[0], wy = iy ? a[1] : 1.0f - a[1], wz = iz ? a[2] : 1.0f - a[2];
                 f += fv * (wx * wy * wz);
             }
             if (valid && prev_valid && f_prev > 0.0f && f <= 0.0f) {
+                if (t - t_prev > 1.5f * dt) { fine_until = t; t = t_prev + dt; continue; }
                 hit = t_prev + (t - t_prev) * (f_prev / (f_prev - f));
                 break;
             }
             prev_valid = valid; f_prev = f; t_prev = t;
-            t += dt;
+            t += (valid && f >= 1.0f && t > fine_until && coarse > dt) ? coarse : dt;
         }
         out[v * W + u] = hit;
     }

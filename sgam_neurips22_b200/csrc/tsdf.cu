@@ -6,8 +6,9 @@
 // follows the published algorithm of that version (see oracle/csrc/tsdf_oracle.c, to which these kernels are
 // bit-exact); the B200 re-design is
 //   * a DENSE grid of 16^3-voxel units in HBM (a few GB of the 180 GB) instead of a host-side hash of units: a unit
-//     is "opened" by stamping it, every unit is one contiguous 32 KB block, one CTA integrates one unit with fully
-//     coalesced 8-byte accesses, no allocation, no host round trip, no atomics, deterministic;
+//     is "opened" by stamping it (the first stamper queues it on the frame's work list), every unit is one contiguous
+//     32 KB block swept by one CTA with fully coalesced 8-byte accesses, no allocation, no host round trip,
+//     deterministic results;
 //   * the target depth is ray-cast straight from the volume (one thread per pixel, trilinear samples, empty units
 //     skipped) instead of marching cubes + mesh upload + rasterisation every step.
 // All three kernels are HBM / L2 latency bound integer-and-fp32 work; compiled with --fmad=false so that every
@@ -35,7 +36,7 @@ __device__ __forceinline__ long long unit_index(const Grid &g, int ux, int uy, i
 // ScalableTSDFVolume::Integrate, first half: one thread per strided depth sample opens the units around its point.
 __global__ void __launch_bounds__(256)
 tsdf_touch_kernel(const float *__restrict__ depth, int H, int W, Pose34d c2w, Intr K, int stride, float depth_trunc,
-                  Grid g, uint32_t *__restrict__ stamp, uint32_t frame) {
+                  Grid g, uint32_t *__restrict__ stamp, uint32_t frame, int *__restrict__ work) {
     const int sw = (W + stride - 1) / stride, sh = (H + stride - 1) / stride;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= sw * sh) return;
@@ -56,60 +57,68 @@ tsdf_touch_kernel(const float *__restrict__ depth, int H, int W, Pose34d c2w, In
         for (int uy = lo[1]; uy <= hi[1]; ++uy)
             for (int uz = lo[2]; uz <= hi[2]; ++uz) {
                 const long long u = unit_index(g, ux, uy, uz);
-                if (u >= 0) stamp[u] = frame;                  // idempotent: every writer stores the same value
+                if (u < 0) continue;
+                // the first thread to stamp a unit this frame queues it; the list order varies from run to run but the
+                // units are disjoint, so the result does not
+                if (atomicExch(stamp + u, frame) != frame) work[1 + atomicAdd(work, 1)] = (int)u;
             }
 }
 
-// UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier: one CTA per unit opened for `frame`;
-// thread (lx,ly) walks lz with the incremental camera-space update Open3D uses.
+// UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier over the frame's work list (work[0] units at
+// work[1..]); a fixed grid of CTAs strides over the list, so the load is balanced and no empty CTA is launched.
+// Per unit the CTA sweeps lx = 0..15; thread (ly, lz) owns one voxel of the 16x16 slab, so the 256 threads read and
+// write 2 KB of contiguous (tsdf, weight) pairs.  Open3D walks z incrementally (pc += R[:,2] * voxel_length per
+// step); each thread replays its lz additions so that the rounding is the same.
 __global__ void __launch_bounds__(256)
 tsdf_integrate_kernel(const float *__restrict__ depth, const float *__restrict__ rgb, int H, int W, Pose34f w2c, Intr Kd,
-                      float depth_trunc, Grid g, const uint32_t *__restrict__ stamp, uint32_t frame,
-                      float2 *__restrict__ vol, float *__restrict__ color) {
-    const long long u = blockIdx.x;
-    if (stamp[u] != frame) return;
+                      float depth_trunc, Grid g, const int *__restrict__ work, float2 *__restrict__ vol,
+                      float *__restrict__ color) {
+    const int n_open = work[0];
     const float fx = (float)Kd.fx, fy = (float)Kd.fy, cx = (float)Kd.cx, cy = (float)Kd.cy;
     const float inv_fx = 1.0f / fx, inv_fy = 1.0f / fy;
     const float vl = g.voxel_length, half = vl * 0.5f, trunc = g.sdf_trunc, trunc_inv = 1.0f / trunc;
     const float safe_w = (float)W - 0.0001f, safe_h = (float)H - 0.0001f, unit_len = vl * RES;
-    const int ux = (int)(u % g.nx) + g.ox, uy = (int)((u / g.nx) % g.ny) + g.oy, uz = (int)(u / ((long long)g.nx * g.ny)) + g.oz;
-    const int lx = threadIdx.x >> 4, ly = threadIdx.x & 15;
-    const float p0x = half + vl * (float)lx + (float)ux * unit_len, p0y = half + vl * (float)ly + (float)uy * unit_len,
-                p0z = half + (float)uz * unit_len;
-    float pc[3];
+    const int ly = threadIdx.x >> 4, lz = threadIdx.x & 15;
+    const float inc[3] = {w2c.m[2] * vl, w2c.m[6] * vl, w2c.m[10] * vl};
+    for (int k = blockIdx.x; k < n_open; k += gridDim.x) {
+        const long long u = work[1 + k];
+        const int ux = (int)(u % g.nx) + g.ox, uy = (int)((u / g.nx) % g.ny) + g.oy, uz = (int)(u / ((long long)g.nx * g.ny)) + g.oz;
+        const float p0y = half + vl * (float)ly + (float)uy * unit_len, p0z = half + (float)uz * unit_len;
+        for (int lx = 0; lx < RES; ++lx) {
+            const float p0x = half + vl * (float)lx + (float)ux * unit_len;
+            float pc[3];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) pc[r] = w2c.m[4 * r] * p0x + w2c.m[4 * r + 1] * p0y + w2c.m[4 * r + 2] * p0z + w2c.m[4 * r + 3];
-    const size_t base = (size_t)u * UNIT_VOX + (size_t)(lx * RES + ly) * RES;
-    for (int lz = 0; lz < RES; ++lz) {
-        if (lz > 0) {
+            for (int r = 0; r < 3; ++r) pc[r] = w2c.m[4 * r] * p0x + w2c.m[4 * r + 1] * p0y + w2c.m[4 * r + 2] * p0z + w2c.m[4 * r + 3];
+            for (int s = 0; s < lz; ++s) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) pc[r] += w2c.m[4 * r + 2] * vl;
-        }
-        if (!(pc[2] > 0.0f)) continue;
-        const float u_f = pc[0] * fx / pc[2] + cx + 0.5f, v_f = pc[1] * fy / pc[2] + cy + 0.5f;
-        if (!(u_f >= 0.0001f && u_f < safe_w && v_f >= 0.0001f && v_f < safe_h)) continue;
-        const int pu = (int)u_f, pv = (int)v_f;
-        float d = __ldg(depth + pv * W + pu);
-        if (d >= depth_trunc) d = 0.0f;
-        if (!(d > 0.0f)) continue;
-        const float xx = ((float)pu - cx) * inv_fx, yy = ((float)pv - cy) * inv_fy;
-        const float mult = sqrtf(xx * xx + yy * yy + 1.0f);
-        const float sdf = (d - pc[2]) * mult;
-        if (!(sdf > -trunc)) continue;
-        const float tsdf = fminf(1.0f, sdf * trunc_inv);
-        const size_t v = base + lz;
-        float2 fw = vol[v];
-        const float w = fw.y;
-        fw.x = (fw.x * w + tsdf) / (w + 1.0f);
-        if (color && rgb) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float c8 = rintf((__ldg(rgb + (size_t)(pv * W + pu) * 3 + c) + 1.0f) * 127.5f);
-                color[3 * v + c] = (color[3 * v + c] * w + c8) / (w + 1.0f);
+                for (int r = 0; r < 3; ++r) pc[r] += inc[r];
             }
+            if (!(pc[2] > 0.0f)) continue;
+            const float u_f = pc[0] * fx / pc[2] + cx + 0.5f, v_f = pc[1] * fy / pc[2] + cy + 0.5f;
+            if (!(u_f >= 0.0001f && u_f < safe_w && v_f >= 0.0001f && v_f < safe_h)) continue;
+            const int pu = (int)u_f, pv = (int)v_f;
+            float d = __ldg(depth + pv * W + pu);
+            if (d >= depth_trunc) d = 0.0f;
+            if (!(d > 0.0f)) continue;
+            const float xx = ((float)pu - cx) * inv_fx, yy = ((float)pv - cy) * inv_fy;
+            const float mult = sqrtf(xx * xx + yy * yy + 1.0f);
+            const float sdf = (d - pc[2]) * mult;
+            if (!(sdf > -trunc)) continue;
+            const float tsdf = fminf(1.0f, sdf * trunc_inv);
+            const size_t v = (size_t)u * UNIT_VOX + (size_t)lx * (RES * RES) + threadIdx.x;
+            float2 fw = vol[v];
+            const float w = fw.y;
+            fw.x = (fw.x * w + tsdf) / (w + 1.0f);
+            if (color && rgb) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float c8 = rintf((__ldg(rgb + (size_t)(pv * W + pu) * 3 + c) + 1.0f) * 127.5f);
+                    color[3 * v + c] = (color[3 * v + c] * w + c8) / (w + 1.0f);
+                }
+            }
+            fw.y = w + 1.0f;
+            vol[v] = fw;
         }
-        fw.y = w + 1.0f;
-        vol[v] = fw;
     }
 }
 
@@ -120,11 +129,12 @@ __device__ __forceinline__ float2 fetch(const Grid &g, const uint32_t *__restric
     return __ldg(vol + (size_t)u * UNIT_VOX + (((gx & 15) * RES) + (gy & 15)) * RES + (gz & 15));
 }
 
-// Target depth by ray casting; one thread per pixel, 16x16 pixel tiles so that neighbouring rays share voxels in L1/L2.
-__global__ void __launch_bounds__(256)
+// Target depth by ray casting; one thread per pixel, 8x8 pixel tiles (a warp = 8x4 pixels) so that neighbouring rays
+// share voxels in L1/L2 and diverge little.
+__global__ void __launch_bounds__(64)
 tsdf_raycast_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__restrict__ vol, Pose34f c2w, Intr Kd,
                     float pixel_center, int H, int W, float z_near, float z_far, float step_vox, float *__restrict__ out) {
-    const int u = blockIdx.x * 16 + (threadIdx.x & 15), v = blockIdx.y * 16 + (threadIdx.x >> 4);
+    const int u = blockIdx.x * 8 + (threadIdx.x & 7), v = blockIdx.y * 8 + (threadIdx.x >> 3);
     if (u >= W || v >= H) return;
     const float fx = (float)Kd.fx, fy = (float)Kd.fy, cx = (float)Kd.cx, cy = (float)Kd.cy;
     const float vl = g.voxel_length, inv_vl = 1.0f / vl, dt = step_vox * vl;
@@ -135,7 +145,10 @@ tsdf_raycast_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__
         dw[r] = (c2w.m[4 * r] * dc[0] + c2w.m[4 * r + 1] * dc[1] + c2w.m[4 * r + 2] * dc[2]) * inv_vl;
         ow[r] = c2w.m[4 * r + 3] * inv_vl - 0.5f;
     }
-    float t = z_near, t_prev = 0.0f, f_prev = 0.0f, hit = 0.0f;
+    // observed free space (tsdf clamped at +1: every integrating view saw the surface >= sdf_trunc further along its
+    // ray) is crossed in coarse steps of 0.8 sdf_trunc of ray length; a sign change found by a coarse step is re-walked
+    const float coarse = 0.8f * g.sdf_trunc / sqrtf(dc[0] * dc[0] + dc[1] * dc[1] + 1.0f);
+    float t = z_near, t_prev = 0.0f, f_prev = 0.0f, hit = 0.0f, fine_until = -1.0f;
     bool prev_valid = false;
     int guard = 0;
     while (t <= z_far && guard++ < 100000) {
@@ -158,22 +171,38 @@ tsdf_raycast_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__
             continue;
         }
         const float a[3] = {p[0] - fl[0], p[1] - fl[1], p[2] - fl[2]};
+        // the 8 trilinear corners: all loads are issued before any is used (the kernel is L2-latency bound); when the
+        // 2x2x2 cell lies inside the base unit (82 % of the samples) they are 8 fixed offsets from one address
+        float2 fw[8];
+        const int l0 = b[0] & 15, l1 = b[1] & 15, l2 = b[2] & 15;
+        if (l0 < 15 && l1 < 15 && l2 < 15) {
+            const float2 *cell = vol + (size_t)unit * UNIT_VOX + ((l0 * RES) + l1) * RES + l2;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) fw[c] = __ldg(cell + (c & 1) * RES * RES + ((c >> 1) & 1) * RES + (c >> 2));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) fw[c] = fetch(g, stamp, vol, b[0] + (c & 1), b[1] + ((c >> 1) & 1), b[2] + (c >> 2));
+        }
         float f = 0.0f;
         bool valid = true;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 8; ++c) {
             const int ix = c & 1, iy = (c >> 1) & 1, iz = c >> 2;
-            const float2 fw = fetch(g, stamp, vol, b[0] + ix, b[1] + iy, b[2] + iz);
-            if (!(fw.y > 0.0f)) { valid = false; break; }
+            valid = valid && (fw[c].y > 0.0f);
             const float wx = ix ? a[0] : 1.0f - a[0], wy = iy ? a[1] : 1.0f - a[1], wz = iz ? a[2] : 1.0f - a[2];
-            f += fw.x * (wx * wy * wz);
+            f += fw[c].x * (wx * wy * wz);
         }
         if (valid && prev_valid && f_prev > 0.0f && f <= 0.0f) {
+            if (t - t_prev > 1.5f * dt) {               // overshot with a coarse step: walk the interval finely
+                fine_until = t;
+                t = t_prev + dt;
+                continue;
+            }
             hit = t_prev + (t - t_prev) * (f_prev / (f_prev - f));
             break;
         }
         prev_valid = valid; f_prev = f; t_prev = t;
-        t += dt;
+        t += (valid && f >= 1.0f && t > fine_until && coarse > dt) ? coarse : dt;
     }
     out[v * W + u] = hit;
 }
@@ -267,8 +296,8 @@ extern "C" size_t sgam_tsdf_volume_bytes(int nx, int ny, int nz, int with_color)
 extern "C" int sgam_tsdf_integrate(const float *depth, const float *rgb, int H, int W, const double *host_cam2world,
                                    const float *host_world2cam, const double *host_K, int stride, float depth_trunc,
                                    int ox, int oy, int oz, int nx, int ny, int nz, float voxel_length, float sdf_trunc,
-                                   uint32_t *stamp, uint32_t frame, float *vol, float *color, void *stream) {
-    SGAM_REQUIRE(depth && host_cam2world && host_world2cam && host_K && stamp && vol, "tsdf_integrate: null pointer");
+                                   uint32_t *stamp, uint32_t frame, int *work, float *vol, float *color, void *stream) {
+    SGAM_REQUIRE(depth && host_cam2world && host_world2cam && host_K && stamp && work && vol, "tsdf_integrate: null pointer");
     SGAM_REQUIRE(H > 0 && W > 0 && stride > 0 && frame != 0, "tsdf_integrate: bad H/W/stride, or frame stamp 0");
     SGAM_REQUIRE((color == nullptr) == (rgb == nullptr), "tsdf_integrate: rgb and color go together");
     if (int rc = check_grid("tsdf_integrate", nx, ny, nz, voxel_length, sdf_trunc)) return rc;
@@ -277,10 +306,10 @@ extern "C" int sgam_tsdf_integrate(const float *depth, const float *rgb, int H, 
     Pose34d c2w; Pose34f w2c; Intr K{host_K[0], host_K[1], host_K[2], host_K[3]};
     for (int i = 0; i < 12; ++i) { c2w.m[i] = host_cam2world[i]; w2c.m[i] = host_world2cam[i]; }
     const int samples = ((W + stride - 1) / stride) * ((H + stride - 1) / stride);
-    tsdf_touch_kernel<<<cdiv(samples, 256), 256, 0, s>>>(depth, H, W, c2w, K, stride, depth_trunc, g, stamp, frame);
+    SGAM_CUDA_OK(cudaMemsetAsync(work, 0, sizeof(int), s));
+    tsdf_touch_kernel<<<cdiv(samples, 256), 256, 0, s>>>(depth, H, W, c2w, K, stride, depth_trunc, g, stamp, frame, work);
     SGAM_LAUNCH_OK();
-    tsdf_integrate_kernel<<<(unsigned)((long long)nx * ny * nz), 256, 0, s>>>(depth, rgb, H, W, w2c, K, depth_trunc, g, stamp, frame,
-                                                                              reinterpret_cast<float2 *>(vol), color);
+    tsdf_integrate_kernel<<<148 * 4, 256, 0, s>>>(depth, rgb, H, W, w2c, K, depth_trunc, g, work, reinterpret_cast<float2 *>(vol), color);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
@@ -295,7 +324,7 @@ extern "C" int sgam_tsdf_raycast(const uint32_t *stamp, const float *vol, int ox
     Grid g{ox, oy, oz, nx, ny, nz, voxel_length, sdf_trunc};
     Pose34f c2w; Intr K{host_K[0], host_K[1], host_K[2], host_K[3]};
     for (int i = 0; i < 12; ++i) c2w.m[i] = host_cam2world[i];
-    tsdf_raycast_kernel<<<dim3(cdiv(W, 16), cdiv(H, 16)), 256, 0, (cudaStream_t)stream>>>(
+    tsdf_raycast_kernel<<<dim3(cdiv(W, 8), cdiv(H, 8)), 64, 0, (cudaStream_t)stream>>>(
         g, stamp, reinterpret_cast<const float2 *>(vol), c2w, K, pixel_center, H, W, z_near, z_far, step_vox, out);
     SGAM_LAUNCH_OK();
     return SGAM_OK;

@@ -60,6 +60,7 @@ class TSDFVolume:
         self.stamp = torch.zeros(n, dtype=torch.int32, device=self.device)           # u32 on the device side
         self.vol = torch.zeros(n, UNIT_RES ** 3, 2, device=self.device)
         self.color = torch.zeros(n, UNIT_RES ** 3, 3, device=self.device) if with_color else None
+        self.work = torch.zeros(n + 1, dtype=torch.int32, device=self.device)        # per-frame list of opened units
         self.frame = 0
 
     # the grid arguments every entry point takes
@@ -92,7 +93,7 @@ class TSDFVolume:
         _lib.check(lib.sgam_tsdf_integrate(depth.data_ptr(), None if rgb is None else rgb.data_ptr(), H, W,
                                            c2w.ctypes.data, w2c32.ctypes.data, k4.ctypes.data, self.stride,
                                            ctypes.c_float(depth_trunc), *self._grid(), self.stamp.data_ptr(),
-                                           ctypes.c_uint32(self.frame), self.vol.data_ptr(),
+                                           ctypes.c_uint32(self.frame), self.work.data_ptr(), self.vol.data_ptr(),
                                            None if rgb is None else self.color.data_ptr(), _stream()), "sgam_tsdf_integrate")
 
     def render_depth(self, K, world2cam, H, W, pixel_center=0.5, z_near=0.05, z_far=20.0, step_vox=0.5):
