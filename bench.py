@@ -282,7 +282,8 @@ def main():
             y = fn(*a, **kw)
             e1.record()
             shp = tuple(a[0][0].shape) + tuple((a[1][0] if isinstance(a[1], tuple) else a[1]).shape)
-            gemm_events.append((e0, e1, flops_of(a, kw, y), fn.__name__, shp, {k: v for k, v in kw.items() if isinstance(v, (int, float, bool))}))
+            gemm_events.append((e0, e1, flops_of(a, kw, y), fn.__name__, shp, {k: v for k, v in kw.items() if isinstance(v, (int, float, bool))},
+                                tensor_bytes(a, kw, y)))
             return y
         return wrapper
 
@@ -290,6 +291,17 @@ def main():
         while isinstance(y, (tuple, list)):
             y = y[0]
         return y
+
+    def tensor_bytes(a, kw, y):                    # algorithmic HBM bytes of one launch: every operand / result tensor once
+        seen, total, stack = set(), 0, [a[0], a[1], y, kw.get("residual"), kw.get("bias_m")]
+        while stack:
+            t = stack.pop()
+            if isinstance(t, (tuple, list)):
+                stack.extend(t)
+            elif torch.is_tensor(t) and t.data_ptr() not in seen:
+                seen.add(t.data_ptr())
+                total += t.numel() * t.element_size()
+        return total
 
     def conv_flops(a, kw, y):                      # 2 * output elements (Cout incl.) * K
         w = a[1][0] if isinstance(a[1], tuple) else a[1]
@@ -319,6 +331,12 @@ def main():
                 t = ev[0].elapsed_time(ev[1])
                 f.write(f"{ev[3]}\t{ev[4]}\t{ev[5]}\t{ev[2] / 1e9:.2f}\t{t:.4f}\t{ev[2] / t / 1e9:.1f}\n")
     conv_tflops = conv_flops_total / (conv_ms * 1e-3) / 1e12
+    gemm_alg_bytes = sum(ev[6] for ev in gemm_events) / max(1, len(gemm_events))
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and ds == "clevr-infinite" and B == 8 and res == 256:      # the configuration the capture was taken on
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     nsplit = eng.nsplit if eng.mode == "tc" else 1
 
     def solo(fn, n=20):
@@ -402,6 +420,32 @@ def main():
         finally:
             os.chdir(cwd)
 
+    # ---------------- B trajectories in lock-step through the real scene loop (TrajectoryBatch = the configs[3] API) -----
+    traj_batch = None
+    if rank == 0 and B > 1:
+        import tempfile
+        from sgam_neurips22_b200.scene_batch import TrajectoryBatch
+        rng = np.random.default_rng(1)
+        lo, hi = synthetic.DATASETS[ds]["depth"]
+        yy, xx = np.meshgrid(np.linspace(0, 1, 256), np.linspace(0, 1, 256), indexing="ij")
+        seeds = [(rng.integers(0, 256, (256, 256, 3)).astype(np.uint8),
+                  (lo + (hi - lo) * (0.5 + 0.3 * np.sin(3 * xx + t) * np.cos(2 * yy))).astype(np.float32)) for t in range(B)]
+        dim = (4, 5) if ds == "clevr-infinite" else (20, 1)
+        tb = TrajectoryBatch(model, ds, seeds, micro_batch=B, output_dim=dim, output_root=tempfile.mkdtemp(prefix="sgam_bench_tb_"))
+        skip = 4
+        for i in range(tb.n_steps):
+            if i == skip:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            tb.step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        traj_batch = {"value": B * (tb.n_steps - skip) / dt, "unit": UNIT, "ms_per_step": 1000.0 * dt / (tb.n_steps - skip),
+                      "trajectories": B, "steps": tb.n_steps - skip,
+                      "note": "TrajectoryBatch.step: the per-GPU trajectories advance in lock-step through InfiniteSceneGeneration's own "
+                              "source selection / batch preparation and ONE batched get_x + forward per step; per-GPU wall clock on rank 0"}
+        del tb
+
     # ---------------- final map all-gather (the only collective; outside the frames/sec region) ----------------------
     poses = torch.zeros(B, 12, dtype=torch.float64)
     ag_ms = None
@@ -422,7 +466,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv + attention products)", "bound": "tensor",
                          "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops"],
-                         "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": gemm_alg_bytes,
+                         "peak_source": peaks["source"] + ", sustained bf16",
                          "launches_per_step": len(gemm_events), "share_of_step": conv_ms / (ms / args.steps),
                          "flops_per_step": conv_flops_total, "mma_issue_tflops": conv_tflops * nsplit,
                          "frac_mma_issue": conv_tflops * nsplit / peaks["tflops"],
@@ -445,6 +490,8 @@ def main():
             line["single_trajectory"] = single
         if scene_loop is not None:
             line["scene_loop"] = scene_loop
+        if traj_batch is not None:
+            line["trajectory_batch"] = traj_batch
         if ag_ms is not None:
             line["allgather_ms"] = ag_ms
             line["allgather_bytes_per_rank"] = int(B * sdist.record_bytes(res, res))

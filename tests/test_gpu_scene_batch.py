@@ -1,0 +1,70 @@
+"""GPU tests of the lock-step trajectory batch (BASELINE.json configs[3]: independent trajectories sharded over
+ranks): a trajectory's frames do not depend on how many ranks share the job, the batched step agrees with the
+single-trajectory scene loop, and the final map assembles every local frame."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def seeds(n, lo=8.0, hi=15.0, res=256):
+    out = []
+    for t in range(n):
+        rng = np.random.default_rng(100 + t)
+        yy, xx = np.meshgrid(np.linspace(0, 1, res), np.linspace(0, 1, res), indexing="ij")
+        depth = (lo + (hi - lo) * (0.5 + 0.3 * np.sin(3 * xx + t) * np.cos(2 * yy))).astype(np.float32)
+        out.append((rng.integers(0, 256, (res, res, 3)).astype(np.uint8), depth))
+    return out
+
+
+@pytest.fixture(scope="module")
+def model():
+    from sgam_neurips22_b200 import synthetic
+    from sgam_neurips22_b200.model import VQModel
+    return synthetic.randomize_weights(VQModel(**synthetic.model_kwargs("clevr-infinite")), seed=0).to("cuda:0").eval()
+
+
+def run(model, tmp, name, **kw):
+    from sgam_neurips22_b200.scene_batch import TrajectoryBatch
+    tb = TrajectoryBatch(model, "clevr-infinite", seeds(4), micro_batch=2, output_dim=(2, 2), output_root=str(tmp / name), **kw)
+    tb.scene_expansion()
+    rgb, depth, poses = tb.local_records()
+    return tb, rgb.cpu().numpy(), depth.cpu().numpy(), poses.numpy()
+
+
+def test_trajectory_frames_do_not_depend_on_the_rank_count(model, tmp_path):
+    tb, rgb, depth, poses = run(model, tmp_path, "w1")
+    assert tb.ids == [0, 1, 2, 3] and rgb.shape == (16, 256, 256, 3) and depth.shape == (16, 256, 256)
+    per_traj = lambda a, k: a[4 * k: 4 * k + 4]
+    for rank in range(2):                                                # the same job on two ranks, run one after the other
+        tbr, rgb_r, depth_r, poses_r = run(model, tmp_path, f"w2r{rank}", rank=rank, world_size=2)
+        assert tbr.ids == [rank, rank + 2]
+        for k, t in enumerate(tbr.ids):
+            assert np.array_equal(per_traj(rgb_r, k), per_traj(rgb, t)), f"trajectory {t} differs between 1 and 2 ranks"
+            assert np.array_equal(per_traj(depth_r, k), per_traj(depth, t))
+            assert np.array_equal(per_traj(poses_r, k), per_traj(poses, t))
+    # trajectories are really different scenes
+    assert not np.array_equal(per_traj(rgb, 0)[1], per_traj(rgb, 1)[1])
+
+
+def test_batched_step_agrees_with_the_single_trajectory_loop(model, tmp_path, monkeypatch):
+    from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration
+    from sgam_neurips22_b200.scene_batch import TrajectoryBatch
+    monkeypatch.chdir(tmp_path)
+    sf = seeds(3)
+    tb = TrajectoryBatch(model, "clevr-infinite", sf, micro_batch=3, output_dim=(2, 2))
+    tb.step()
+    for t in (0, 2):
+        solo = InfiniteSceneGeneration(model, "clevr-infinite", seed_frame=sf[t], seed_index=50 + t, output_dim=(2, 2))
+        tgt = solo.next_pose(solo.curr)
+        solo.one_step_prediction(tgt, save_res_to_disk=False)
+        rgb_b, d_b = tb.pipes[t]._frames[tuple(tgt)]
+        rgb_s, d_s = solo._frames[tuple(tgt)]
+        du8 = torch.round((rgb_b - rgb_s) * 127.5).abs()
+        assert float(du8.max()) <= 1 and float((du8 > 0).float().mean()) < 1e-2       # uint8 lattice: rare off-by-one
+        # metric depth is 1 / (affine code): compare where the decoder's 1e-3 tolerance lives, in inverse depth
+        assert float((1.0 / d_b - 1.0 / d_s).abs().max()) < 1e-3 * (1 / 7 - 1 / 16)
+    xyz, col, (rgb, depth, poses) = tb.gather_map()
+    assert xyz.shape == (3 * 2 * 65536, 3) and col.shape == xyz.shape and bool(torch.isfinite(xyz).all())
+    assert rgb.shape[0] == 6 and poses.shape == (6, 12)
