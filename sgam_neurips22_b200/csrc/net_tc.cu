@@ -51,7 +51,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // swizzle atoms need 1024-B alignment
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float stat_s[4][BN / 4 * 2];        // [epilogue warp][group in tile][sum, sumsq]  (cpg >= 4)
+    __shared__ float stat_s[4][BN / 4 * 2];
+    __shared__ __align__(16) EpiStage epi_stage;      // per-warp transpose tiles of the coalesced epilogue stores        // [epilogue warp][group in tile][sum, sumsq]  (cpg >= 4)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = p.taps * p.kblocks_per_tap;
@@ -157,7 +158,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                 const int r = mt * 128 + q * 32 + lane;                 // row of the box; TMEM lane = r % 128
                 const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * BN);
                 const long long slot = ((long long)b * (p.tiles_x * p.tiles_y) + m_tile) * MT + mt;
-                epilogue_rows<BN>(p, tmem_acc, r, b, ty * p.BH, tx * p.BW, n0, mn % p.tiles_n, ksp, slot, stat_s, q, lane);
+                epilogue_rows<BN>(p, tmem_acc, r, b, ty * p.BH, tx * p.BW, n0, mn % p.tiles_n, ksp, slot, stat_s, epi_stage, q, lane);
             }
             // this accumulator set may be overwritten by the MMA warp as soon as all four warps have read it
             tc_fence_before();

@@ -37,8 +37,12 @@ __device__ __forceinline__ uint32_t map_to_cta(const void *local, uint32_t rank)
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
+// Remote arrive with the default (CTA-scope release) semantics.  `.release.cluster` here compiled to MEMBAR.ALL.GPU +
+// ERRBAR, i.e. every epilogue warp waited for all of its global stores to be acknowledged before it could hand the
+// accumulator back (12 % of the stall samples of the QK^T GEMM); the hand-over only has to order the TMEM reads,
+// which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already do.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma2_load_4d(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -90,6 +94,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float stat_s[4][BN / 4 * 2];
+    __shared__ __align__(16) EpiStage epi_stage;      // per-warp transpose tiles of the coalesced epilogue stores
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -189,7 +194,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const long long slot = ((long long)b * (g.tiles_x2 * g.tiles_y2) + m2) * 2 + rank;
-            epilogue_rows<BN>(p, tmem_acc, q * 32 + lane, b, oy0, ox0, n0, n_tile, 0, slot, stat_s, q, lane);
+            epilogue_rows<BN>(p, tmem_acc, q * 32 + lane, b, oy0, ox0, n0, n_tile, 0, slot, stat_s, epi_stage, q, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(map_to_cta(&tmem_empty_bar[acc], 0));

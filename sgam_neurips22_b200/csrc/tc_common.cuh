@@ -133,18 +133,34 @@ __device__ __forceinline__ void chunk_group_sums(const float (&o)[32], bool row_
     }
 }
 
+// Per-warp staging for coalesced output stores: 32 rows x 32 fp32 columns, rows padded to 36 floats (16-byte aligned,
+// conflict-free for 128-bit accesses by quarter-warps), plus the global element offset of each of the warp's rows.
+constexpr int STG_STRIDE = 36;
+struct EpiStage {
+    float tile[4][32 * STG_STRIDE];
+    long long rowoff[4][32];                // row_off of row (32q + i), or -1 when the row is outside the image
+};
+
 // Epilogue of one 128-row accumulator: thread (q, lane) owns box row r (= TMEM lane 32q + lane) and walks the BN
 // columns in 32-wide chunks: VQ tile minimum, split-K partial store, or alpha / bias / residual + fp32 / split-bf16 /
 // NCHW stores + fused GroupNorm partial statistics.  Must be called by all four epilogue warps (named barrier 1).
+// A TMEM lane is an output ROW, so a thread holds 32 consecutive columns of its own row; storing them directly makes
+// every warp-wide store touch 32 rows x 16 bytes (32 half-used sectors; the LSU, not HBM, then bounds the small-K
+// GEMMs).  The finished chunk therefore goes through the warp's staging tile and is written back row-contiguously:
+// 8 lanes x 16 B = one 128-byte line of a row (fp32), 4 lanes x 16 B = one 64-byte segment (bf16 planes).
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_acc, int r, int b, int oy0, int ox0, int n0, int n_tile,
-                                      int ksp, long long slot, float (*stat_s)[BN / 4 * 2], int q, int lane) {
+                                      int ksp, long long slot, float (*stat_s)[BN / 4 * 2], EpiStage &es, int q, int lane) {
     const int ly = r / p.BW, lx = r - ly * p.BW;
     const int oy = oy0 + ly, ox = ox0 + lx;
     const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
     const long long m = (long long)oy * p.Wo + ox;          // row within the batch slice
     const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
     const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
+    float *stg = es.tile[q];
+    __syncwarp();
+    es.rowoff[q][lane] = row_ok ? row_off : -1;
+    __syncwarp();
     if (p.vq_tilemin) {                               // codebook search: per-row minimum of the approximate distances
         const float zz = row_ok ? __ldg(p.vq_zz + m) : 0.0f;
         float best = INFINITY;
@@ -219,21 +235,43 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
             else if (p.cpg == 8) chunk_group_sums<8>(o, row_ok, lane, dst);
             else chunk_group_sums<16>(o, row_ok, lane, dst);
         }
-        if (!row_ok) continue;
-        if (p.D) {
+        if (p.D) {                                    // fp32: stage the chunk, then 4 rows x 128 contiguous bytes per store
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4 *>(p.D + row_off + n + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                *reinterpret_cast<float4 *>(stg + lane * STG_STRIDE + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3), cc = (lane & 7) * 4;
+                const long long off = es.rowoff[q][rr];
+                const float4 val = *reinterpret_cast<const float4 *>(stg + rr * STG_STRIDE + cc);
+                if (off >= 0) *reinterpret_cast<float4 *>(p.D + off + n + cc) = val;
+            }
+            __syncwarp();
         }
-        if (p.D_hi) {
+        if (p.D_hi) {                                 // split bf16: hi words in floats [0,16), lo words in [16,32) of the row
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) split2(o[j], o[j + 1], hi[j / 2], lo[j / 2]);
+            uint32_t *stg_u = reinterpret_cast<uint32_t *>(stg);
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                *reinterpret_cast<uint4 *>(p.D_hi + row_off + n + 2 * j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
-                *reinterpret_cast<uint4 *>(p.D_lo + row_off + n + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                *reinterpret_cast<uint4 *>(stg_u + lane * STG_STRIDE + j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+                *reinterpret_cast<uint4 *>(stg_u + lane * STG_STRIDE + 16 + j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
             }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + (lane >> 2), cc = (lane & 3) * 4;           // cc in 32-bit words = 2 bf16 each
+                const long long off = es.rowoff[q][rr];
+                const uint4 h4 = *reinterpret_cast<const uint4 *>(stg_u + rr * STG_STRIDE + cc);
+                const uint4 l4 = *reinterpret_cast<const uint4 *>(stg_u + rr * STG_STRIDE + 16 + cc);
+                if (off >= 0) {
+                    *reinterpret_cast<uint4 *>(p.D_hi + off + n + 2 * cc) = h4;
+                    *reinterpret_cast<uint4 *>(p.D_lo + off + n + 2 * cc) = l4;
+                }
+            }
+            __syncwarp();
         }
     }
     if (p.stats) {
