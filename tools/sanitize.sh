@@ -14,9 +14,25 @@ x, _, mask, _ = model.get_x(b, ds, return_extrapolation_mask=True, no_depth_rang
 decs, _, pre, quants = model(x, topk=1, extrapolation_mask=mask, get_pre_quantized_feature=True, get_quantized_feature=True)
 rgb, depth = ops.frame_outputs(decs[0][0], ds)
 torch.cuda.synchronize()
-print("step ok", float(decs[0][0].abs().mean()))
+# RGB-D integration kernels on a small volume
+from sgam_neurips22_b200.tsdf import TSDFVolume, frustum_box
+K = np.array([[124.4, 0, 32.0], [0, 124.4, 32.0], [0, 0, 1.0]])
+yy, xx = np.meshgrid(np.linspace(0, 1, 64), np.linspace(0, 1, 64), indexing="ij")
+dm = torch.from_numpy((2.0 + 0.3 * np.sin(4 * xx) * np.cos(3 * yy)).astype(np.float32)).cuda()
+im = torch.rand(64, 64, 3, device="cuda") * 2 - 1
+lo, hi = frustum_box(K, [np.eye(4)], 64, 64, 2.8, pad=0.2)
+vol = TSDFVolume(0.01, 0.03, lo, hi)
+vol.integrate(dm, im, K, np.eye(4)); vol.integrate(dm, im, K, np.eye(4))
+rd = vol.render_depth(K, np.eye(4), 64, 64, z_far=3.0)
+pts, cols = vol.extract_point_cloud()
+torch.cuda.synchronize()
+print("tsdf ok", float(rd.mean()), int(pts.shape[0]))
+import hashlib
+print("step ok", float(decs[0][0].abs().mean()), hashlib.sha256(decs[0][0].cpu().numpy().tobytes()).hexdigest()[:16])
 PY
-for tool in memcheck racecheck synccheck; do
+echo "=== plain run (the sanitizer runs must reproduce this checksum) ==="
+python /tmp/san_step.py 2>&1 | grep -E "step ok|tsdf ok"
+for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
   echo "=== compute-sanitizer --tool $tool ==="
-  timeout -s KILL 900 compute-sanitizer --tool $tool --kernel-regex kns=sgam --kernel-regex kne=at:: python /tmp/san_step.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|step ok|Error|hazard" | head -8
+  timeout -s KILL 900 compute-sanitizer --tool $tool python /tmp/san_step.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|step ok|tsdf ok|Error|hazard" | head -8
 done
