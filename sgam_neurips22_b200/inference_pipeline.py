@@ -81,7 +81,8 @@ class InfiniteSceneGeneration:
     def __init__(self,
                  dynamic_model, data, topk=1, step_size_denom=2, use_rgbd_integration=False, use_discriminator_loss=False,
                  discriminator_loss_weight=0, recon_on_visible=False, offscreen_rendering=True, output_dim=None, seed_index=0,
-                 num_src=None, tsdf_depth_fn=None, template_root="templates", output_root="grid_res", seed_frame=None):
+                 num_src=None, tsdf_depth_fn=None, template_root="templates", output_root="grid_res", seed_frame=None,
+                 image_resolution=(256, 256)):
         self.use_discriminator_loss = use_discriminator_loss
         self.offscreen_rendering = offscreen_rendering
         self.discriminator_loss_weight = discriminator_loss_weight
@@ -95,11 +96,16 @@ class InfiniteSceneGeneration:
         self.tsdf_depth_fn = tsdf_depth_fn
         if data not in ("clevr-infinite", "google_earth"):
             raise NotImplementedError                                      # inference_pipeline.py:55-56
-        self.image_resolution = (256, 256)                                 # :42,47
+        # :42,47 hard-code 256x256; BASELINE.json configs[4] runs GoogleEarth at 512x512, so it is a keyword here
+        self.image_resolution = tuple(int(v) for v in image_resolution)
+        if self.image_resolution[0] % 16 or self.image_resolution[1] % 16:
+            raise ValueError("image_resolution must be a multiple of 16 (the VQGAN down-samples by 16)")
         self.output_dim = ((20, 20) if data == "clevr-infinite" else (100, 1)) if output_dim is None else output_dim
         is_vq = isinstance(dynamic_model, VQModel)
         if data == "clevr-infinite":
-            self.K = np.array([[355.5555, 0, 128], [0, 355.5555, 128], [0, 0, 1]])            # :61-65
+            self.K = np.array([[355.5555, 0, 128], [0, 355.5555, 128], [0, 0, 1]])            # :61-65 (for 256x256)
+            self.K[0] = self.K[0] * self.image_resolution[1] / 256
+            self.K[1] = self.K[1] * self.image_resolution[0] / 256
             self.num_src = (5 if num_src is None else num_src) if is_vq else 1                 # :68
         else:
             self.K = np.array([[497.77774, 0, 256], [0, 497.77774, 256], [0, 0, 1]])          # :83-89

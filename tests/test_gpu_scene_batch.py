@@ -68,3 +68,22 @@ def test_batched_step_agrees_with_the_single_trajectory_loop(model, tmp_path, mo
     xyz, col, (rgb, depth, poses) = tb.gather_map()
     assert xyz.shape == (3 * 2 * 65536, 3) and col.shape == xyz.shape and bool(torch.isfinite(xyz).all())
     assert rgb.shape[0] == 6 and poses.shape == (6, 12)
+
+
+def test_google_earth_512_long_horizon_shape(tmp_path):
+    """BASELINE.json configs[4] shape: GoogleEarth at 512x512 (latent 32x32, attention over 16384 tokens) through the
+    lock-step trajectory loop; the reference hard-codes 256x256 (inference_pipeline.py:42,47), here it is a keyword."""
+    from sgam_neurips22_b200 import synthetic
+    from sgam_neurips22_b200.model import VQModel
+    from sgam_neurips22_b200.scene_batch import TrajectoryBatch
+    ds = "google_earth"
+    model = synthetic.randomize_weights(VQModel(**synthetic.model_kwargs(ds)), seed=0).to("cuda:0").eval()
+    tb = TrajectoryBatch(model, ds, seeds(2, lo=1.4, hi=3.8, res=512), micro_batch=2, output_dim=(3, 1),
+                         output_root=str(tmp_path / "ge512"), image_resolution=(512, 512))
+    assert tb.pipes[0].K[0, 0] == pytest.approx(497.77774) and tb.pipes[0].K[0, 2] == 256
+    tb.scene_expansion()
+    rgb, depth, poses = tb.local_records()
+    assert rgb.shape == (6, 512, 512, 3) and depth.shape == (6, 512, 512) and poses.shape == (6, 12)
+    assert bool(torch.isfinite(depth).all())
+    xyz, col, _ = tb.gather_map()
+    assert xyz.shape == (6 * 512 * 512, 3)
