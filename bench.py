@@ -128,7 +128,7 @@ def run_reference(args, rank):
     fps = args.steps / dt
     cfg = workload_config(args, 1)
     cfg["frames_per_step"] = 1
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -149,7 +149,20 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def emit(line):
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1), so
+    main() points fd 1 at stderr for the whole run and the result goes to the saved descriptor."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -500,7 +513,7 @@ def main():
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{n} frames of the same workload at batch 1 in {dt:.1f} s (torch CPU fp32 oracle port, "
                                               f"{os.cpu_count()} threads; the reference hard-codes batch 1)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
