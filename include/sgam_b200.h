@@ -250,6 +250,14 @@ int sgam_tsdf_extract(const uint32_t *stamp, const float *vol, const float *colo
                       int nx, int ny, int nz, float voxel_length, float sdf_trunc, long long *unit_counts,
                       const long long *unit_offsets, float *xyz, float *rgb, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Final map.  Replaces InfiniteSceneGeneration.prepare_pcd (sgam/inference_pipeline.py:1014-1036) for a stack of
+ * frames: xyz[f,p] = inv(Rt_f) [K^-1 [u v 1]^T depth ; 1] in float64 (numpy dgemm rounding order), colors = u8 / 255.
+ *   depth [F,H,W] fp32; rgb_u8 [F,H,W,3] or NULL; host_Kinv: 9 doubles (HOST); Rt_inv [F,12] doubles (device; rows 0-2
+ *   of the inverse world->camera matrix); xyz [F*H*W,3] f64; colors [F*H*W,3] f64 or NULL. */
+int sgam_unproject_points(const float *depth, const uint8_t *rgb_u8, const double *host_Kinv, const double *Rt_inv,
+                          int F, int H, int W, double *xyz, double *colors, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

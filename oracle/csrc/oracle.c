@@ -245,13 +245,25 @@ void oracle_vq_nearest(const float *z, const float *E, int T, int n_e, int D,
     free(ee);
 }
 
-/* inference_pipeline.py:1014-1036 prepare_pcd: X_w = inv(Rt) [K^-1 [u v 1]^T d ; 1], float64. */
+/* inference_pipeline.py:1014-1036 prepare_pcd: X_w = inv(Rt) [K^-1 [u v 1]^T d ; 1], float64.
+ * numpy's dgemm evaluates the K = 3 / K = 4 dot products as one rounded product followed by fused multiply-adds (same
+ * pattern as the fp32 dot3 above; pinned bit-exact by tests/golden/prepare_pcd_vectors.npz). */
 void oracle_unproject_world(const float *depth, const double *Kinv, const double *Rt_inv, int H, int W, double *xyz) {
     for (int i = 0; i < H; ++i) for (int j = 0; j < W; ++j) {
         size_t p = (size_t)i * W + j;
-        double d = (double)depth[p], c[3], w[3];
-        for (int r = 0; r < 3; ++r) c[r] = d * (Kinv[3 * r] * j + Kinv[3 * r + 1] * i + Kinv[3 * r + 2]);
-        for (int r = 0; r < 3; ++r) w[r] = Rt_inv[4 * r] * c[0] + Rt_inv[4 * r + 1] * c[1] + Rt_inv[4 * r + 2] * c[2] + Rt_inv[4 * r + 3];
-        xyz[p * 3 + 0] = w[0]; xyz[p * 3 + 1] = w[1]; xyz[p * 3 + 2] = w[2];
+        double d = (double)depth[p], c[3];
+        for (int r = 0; r < 3; ++r) {
+            double t = Kinv[3 * r] * (double)j;
+            t = fma(Kinv[3 * r + 1], (double)i, t);
+            t = fma(Kinv[3 * r + 2], 1.0, t);
+            c[r] = d * t;
+        }
+        for (int r = 0; r < 3; ++r) {
+            double t = Rt_inv[4 * r] * c[0];
+            t = fma(Rt_inv[4 * r + 1], c[1], t);
+            t = fma(Rt_inv[4 * r + 2], c[2], t);
+            t = fma(Rt_inv[4 * r + 3], 1.0, t);
+            xyz[p * 3 + r] = t;
+        }
     }
 }

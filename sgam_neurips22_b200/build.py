@@ -22,6 +22,7 @@ SOURCES = {
     "splat.cu": ["--fmad=false"],
     "vq.cu": ["--fmad=false"],
     "tsdf.cu": ["--fmad=false"],
+    "pcd.cu": ["--fmad=false"],
     "net_simt.cu": [],
     "net_tc.cu": [],
     "net_tc2.cu": [],

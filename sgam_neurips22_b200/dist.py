@@ -49,9 +49,17 @@ def gather_scene_map(rgb_u8, depth, poses, group=None):
 
 def unproject_records(rgb_u8, depth, poses, K):
     """prepare_pcd (inference_pipeline.py:1014-1036) for a stack of gathered records: float64 world points [F*H*W,3]
-    and colours in [0,1].  Runs where the tensors live (float64 torch ops: post-loop, outside the hot path)."""
+    and colours in [0,1].  Device records go through the sgam_unproject_points kernel (bit-identical to the
+    reference's numpy); host records (the gloo tests) through the same formula in float64 torch ops."""
     F, H, W = depth.shape
     dev = depth.device
+    if depth.is_cuda:
+        from . import ops
+        Rt = np.tile(np.eye(4), (F, 1, 1))
+        pn = poses.detach().cpu().numpy()
+        Rt[:, :3, :3] = pn[:, :9].reshape(F, 3, 3)
+        Rt[:, :3, 3] = pn[:, 9:]
+        return ops.unproject_points(depth.contiguous(), rgb_u8.contiguous(), K, Rt)
     ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64, device=dev),
                             torch.arange(W, dtype=torch.float64, device=dev), indexing="ij")
     pix = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(H * W, dtype=torch.float64, device=dev)])

@@ -408,6 +408,19 @@ class InfiniteSceneGeneration:
         world = np.linalg.inv(Rt) @ np.concatenate([cam, np.ones((1, h * w))], 0)
         return world[:3].T, color.reshape(h * w, 3) / 255.
 
+    def unproject_frames_on_device(self):
+        """:1038-1062 without the disk round trip: every visited frame of the resident store, in zig-zag order, through
+        the sgam_unproject_points kernel.  Returns device tensors (xyz [P,3] f64, colours [P,3] f64 in [0,1]).  The
+        seed frame carries the depth the splat path uses (for CLEVR: after the second ray->z conversion, :582-590)."""
+        coords = [c for c in self._ordered_grid_coords if tuple(c) in self._frames]
+        rgb = torch.stack([torch.round((self._frames[tuple(c)][0] + 1.0) * 127.5).to(torch.uint8) for c in coords])
+        depth = torch.stack([self._frames[tuple(c)][1] for c in coords]).contiguous()
+        Rt = np.tile(np.eye(4), (len(coords), 1, 1))
+        for k, c in enumerate(coords):
+            node = self.transform_grid[c[0]][c[1]]
+            Rt[k, :3, :3], Rt[k, :3, 3] = node["R"], node["t"]
+        return ops.unproject_points(depth, rgb.contiguous(), self.K, Rt)
+
     def unproject_to_color_point_cloud(self):
         """:1038-1062 from the files on disk (sorted by R_* name)."""
         from PIL import Image

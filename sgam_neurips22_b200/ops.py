@@ -110,6 +110,30 @@ def inverse_warp(src_rgb, src_depth, tgt_depth, Kinv_tgt, proj, channels_last=Fa
     return (out, best) if want_best else out
 
 
+def unproject_points(depth, rgb_u8, K, Rt):
+    """prepare_pcd (inference_pipeline.py:1014-1036) for a stack of frames on the device: depth [F,H,W] fp32,
+    rgb_u8 [F,H,W,3] uint8 or None, K 3x3, Rt [F,4,4] world->camera (host, float64) -> xyz [F*H*W,3] f64 (and
+    colours [F*H*W,3] f64 in [0,1])."""
+    import numpy as np
+    lib = _lib.load()
+    _chk(depth, name="depth")
+    F, H, W = depth.shape
+    if rgb_u8 is not None:
+        _chk(rgb_u8, torch.uint8, "rgb_u8")
+    Kinv = np.ascontiguousarray(np.linalg.inv(np.asarray(K, np.float64)))
+    Rt = np.asarray(Rt, np.float64).reshape(F, 4, 4)
+    Rt_inv = torch.from_numpy(np.ascontiguousarray(np.stack([np.linalg.inv(m)[:3] for m in Rt]))).to(depth.device)
+    xyz = torch.empty(F * H * W, 3, dtype=torch.float64, device=depth.device)
+    col = torch.empty(F * H * W, 3, dtype=torch.float64, device=depth.device) if rgb_u8 is not None else None
+    for f0 in range(0, F, 65535):                                           # frames ride in grid.y
+        f1 = min(F, f0 + 65535)
+        _lib.check(lib.sgam_unproject_points(depth[f0:f1].data_ptr(), None if rgb_u8 is None else rgb_u8[f0:f1].data_ptr(),
+                                             Kinv.ctypes.data, Rt_inv[f0:f1].data_ptr(), f1 - f0, H, W,
+                                             xyz[f0 * H * W:].data_ptr(), None if col is None else col[f0 * H * W:].data_ptr(),
+                                             _stream()), "sgam_unproject_points")
+    return (xyz, col) if rgb_u8 is not None else xyz
+
+
 def frame_outputs(dec, dataset, rgb_u8=None, depth=None, want_src_rgb=False):
     """inference_pipeline.py:893-911: dec [B,4,H,W] -> uint8 RGB [B,H,W,3], metric depth [B,H,W]
     (+ the fp32 source image u8/127.5-1 a later step would re-load, inference_pipeline.py:534)."""

@@ -387,3 +387,29 @@ def test_vqmodel_topk_sampling_api(state_dicts):
     pinned = ~m[:, :, ::16, ::16].expand(1, 256, 4, 4)
     for s in range(3):
         assert torch.equal(quants[:, s][pinned], nearest[:, 0][pinned])
+
+
+def test_unproject_points_matches_reference_prepare_pcd_bit_for_bit():
+    """Final map: the kernel against the vectors of the unmodified reference method and
+    against the oracle on a full-size frame stack."""
+    import os
+    from oracle import native
+    from sgam_neurips22_b200 import ops
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prepare_pcd_vectors.npz"))
+    for n in ("clevr", "ge"):
+        xyz, col = ops.unproject_points(torch.from_numpy(g[n + "_depth"])[None].cuda(), torch.from_numpy(g[n + "_color"])[None].cuda(),
+                                        g[n + "_K"], g[n + "_Rt"][None])
+        assert np.array_equal(xyz.cpu().numpy(), g[n + "_points"])
+        assert np.array_equal(col.cpu().numpy(), g[n + "_colors"])
+    rng = np.random.default_rng(5)
+    F, H, W = 3, 256, 256
+    depth = rng.uniform(7, 16, (F, H, W)).astype(np.float32)
+    K = np.array([[355.5555, 0, 128], [0, 355.5555, 128], [0, 0, 1]])
+    Rts = []
+    for f in range(F):
+        A = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+        Rt = np.eye(4); Rt[:3, :3] = A; Rt[:3, 3] = rng.uniform(-20, 20, 3)
+        Rts.append(Rt)
+    xyz = ops.unproject_points(torch.from_numpy(depth).cuda(), None, K, np.stack(Rts)).cpu().numpy().reshape(F, H * W, 3)
+    for f in range(F):
+        assert np.array_equal(xyz[f], native.unproject_world(depth[f], np.linalg.inv(K), np.linalg.inv(Rts[f])))

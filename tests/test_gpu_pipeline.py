@@ -88,6 +88,22 @@ def test_scene_expansion_writes_reference_layout_and_point_cloud(models, tmp_pat
     assert len(srcs) >= 3
 
 
+def test_device_point_cloud_equals_the_disk_round_trip(models, tmp_path, monkeypatch):
+    """unproject_frames_on_device (resident frame store -> sgam_unproject_points) reproduces, bit for bit, the
+    reference-style unproject_to_color_point_cloud over the files it wrote (inference_pipeline.py:1038-1062)."""
+    from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration
+    monkeypatch.chdir(tmp_path)
+    ds = "google_earth"
+    rng = np.random.default_rng(4)
+    pipe = InfiniteSceneGeneration(models(ds), ds, seed_frame=seed_frame(rng, 1.4, 3.8), output_dim=(3, 1))
+    pipe.scene_expansion()
+    xyz_disk, col_disk = pipe.unproject_to_color_point_cloud()           # generated frames only (the seed has no R_/t_ file)
+    xyz_dev, col_dev = pipe.unproject_frames_on_device()                  # seed frame first, then the generated ones
+    assert xyz_dev.shape == (3 * 65536, 3)
+    assert np.array_equal(xyz_dev[65536:].cpu().numpy(), xyz_disk)
+    assert np.array_equal(col_dev[65536:].cpu().numpy(), col_disk)
+
+
 def test_rgbd_integration_branch_with_supplied_depth(models, tmp_path, monkeypatch):
     """configs[2]-shaped loop: use_rgbd_integration=True with the target depth supplied (Open3D stand-in)."""
     from oracle import native

@@ -117,3 +117,14 @@ def test_full_step_256(golden, state_dicts, ds):
     assert d.max() <= 1 and (d > 0).mean() < 1e-3
     ok = np.abs(golden[f"step256.{ds}.depth_sub"]) < 50
     assert np.allclose(r["depth"][::4, ::4][ok], golden[f"step256.{ds}.depth_sub"][ok], rtol=1e-3, atol=1e-3)
+
+
+def test_prepare_pcd_oracle_is_bit_exact_to_the_reference():
+    """inference_pipeline.py:1014-1036 (prepare_pcd) run by the unmodified reference (tests/golden/make_golden_pcd.py)."""
+    import os
+    from oracle import native
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prepare_pcd_vectors.npz"))
+    for n in ("clevr", "ge"):
+        xyz = native.unproject_world(g[n + "_depth"], np.linalg.inv(g[n + "_K"]), np.linalg.inv(g[n + "_Rt"]))
+        assert np.array_equal(xyz, g[n + "_points"])
+        assert np.array_equal(g[n + "_color"].reshape(-1, 3) / 255.0, g[n + "_colors"])
