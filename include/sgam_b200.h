@@ -194,13 +194,19 @@ int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int strid
  * Output fp32 y (NHWC, or [B,Cout,Ho,Wo] when out_nchw: the decoder head) and/or split-bf16 y_hi/y_lo. */
 int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                    const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
-                   int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws, void *stream);
+                   int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws,
+                   double *splitk_gn_partial, void *stream);
 
 /* Split-K for under-filled grids (low-resolution layers, single-trajectory batches): when splitk_ws is given and
  * sgam_conv2d_tc_splitk_floats(...) > 0 floats, the K loop is divided among CTAs, partial tiles go to the workspace
  * and a reduce kernel adds them in split order with bias / residual (deterministic; fp32 NHWC output only, no fused
  * GroupNorm statistics). */
 long long sgam_conv2d_tc_splitk_floats(int B, int H, int W, int Cin, int Cout, int ksize, int stride);
+/* When the K loop is split and splitk_gn_partial ([B][sgam_gn_splits(Ho*Wo)][32][2] f64) is given (Cout % 128 == 0), the
+ * reduce kernel also accumulates the GroupNorm partial sums of the finished tensor -- the layout sgam_groupnorm_split
+ * computes with its own statistics pass -- and sgam_groupnorm_split_apply consumes them without re-reading statistics. */
+int sgam_groupnorm_split_apply(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
+                               const double *partial, int B, long long HW, int C, int swish, void *stream);
 
 /* GroupNorm statistics fused into the conv epilogue: when gn_partial (sgam_tc_gn_partial_floats(B,Ho,Wo) floats) is
  * passed to sgam_conv2d_tc, each pixel block writes the per-group sum / sum of squares of the finished output, and

@@ -251,6 +251,53 @@ splitk_reduce_kernel(const float *__restrict__ ws, long long split_stride, int k
     }
 }
 
+// The same reduction fused with the GroupNorm statistics of the finished tensor (the split-K layers are the small ones,
+// where a separate statistics launch costs as much as the reduction): grid (S, B) and the thread -> (channel quad, pixel
+// lane) mapping, accumulation order and fp64 group reduction of gn_stats_kernel (net_simt.cu), so D and the partial
+// sums are bit-identical to splitk_reduce_kernel followed by gn_stats_kernel.  C % 128 == 0, C <= 1024.
+__global__ void __launch_bounds__(256)
+splitk_reduce_stats_kernel(const float *__restrict__ ws, long long split_stride, int ksplit, const float *__restrict__ bias,
+                           const float *__restrict__ R, float *__restrict__ D, double *__restrict__ partial, long long HW, int C, int S) {
+    __shared__ double red[256][2];
+    const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
+    const int CQ = C / 4, PL = 256 / CQ, cq = tid % CQ, pl = tid / CQ;
+    const long long chunk = (HW + S - 1) / S, pbeg = s * chunk, pend = min(HW, pbeg + chunk);
+    float sum = 0.f, sq = 0.f;
+    if (pl < PL) {
+        const long long base = (long long)b * HW * CQ + cq;               // float4 index of (b, pixel 0, channel quad cq)
+        const float4 bv = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long p = pbeg + pl; p < pend; p += PL) {
+            const long long e = base + p * CQ;
+            float4 a = __ldg(reinterpret_cast<const float4 *>(ws) + e);
+            for (int k = 1; k < ksplit; ++k) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (long long)k * split_stride) + e);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            if (bias) { a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w; }
+            if (R) {
+                const float4 r = __ldg(reinterpret_cast<const float4 *>(R) + e);
+                a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+            }
+            reinterpret_cast<float4 *>(D)[e] = a;
+            sum += (a.x + a.y) + (a.z + a.w);
+            sq = fmaf(a.x, a.x, sq); sq = fmaf(a.y, a.y, sq); sq = fmaf(a.z, a.z, sq); sq = fmaf(a.w, a.w, sq);
+        }
+    }
+    red[tid][0] = (double)sum; red[tid][1] = (double)sq;
+    __syncthreads();
+    if (tid < 32) {
+        const int nq = (C / 32) / 4;
+        double a = 0.0, q = 0.0;
+        for (int l = 0; l < PL; ++l)
+            for (int k = 0; k < nq; ++k) {
+                const int t = l * CQ + tid * nq + k;
+                a += red[t][0]; q += red[t][1];
+            }
+        double *dst = partial + (((size_t)b * S + s) * 32 + tid) * 2;
+        dst[0] = a; dst[1] = q;
+    }
+}
+
 // Split the K loop when the (pixel block x column tile) grid would leave most SMs idle (low-resolution layers,
 // single-trajectory batches): returns the number of splits (1 = none).
 int pick_ksplit(long long mn_tiles, int num_kb) {
@@ -305,7 +352,8 @@ extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize
 
 extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                               const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
-                              int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws, void *stream) {
+                              int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws,
+                              double *splitk_gn_partial, void *stream) {
     SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && (y || (y_hi && y_lo)), "conv2d_tc: null pointer");
     SGAM_REQUIRE(!gn_partial || (Cout % 128 == 0 && Cout <= 512 && !out_nchw), "conv2d_tc: fused GroupNorm statistics need Cout in {128,256,384,512}");
     SGAM_REQUIRE(stride == 1 || stride == 2, "conv2d_tc: stride %d", stride);
@@ -364,6 +412,14 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
         int rc2 = launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, (cudaStream_t)stream);
         if (rc2) return rc2;
         const long long total_q = p.split_stride / 4;
+        if (splitk_gn_partial && Cout % 128 == 0 && Cout <= 1024) {          // reduction + GroupNorm statistics in one pass
+            const long long HW = (long long)Ho * Wo;
+            const int S = sgam_gn_splits(HW);
+            splitk_reduce_stats_kernel<<<dim3(S, B), 256, 0, (cudaStream_t)stream>>>(splitk_ws, p.split_stride, p.ksplit, bias, residual, y,
+                                                                                     splitk_gn_partial, HW, Cout, S);
+            SGAM_LAUNCH_OK();
+            return SGAM_OK;
+        }
         const unsigned blocks = (unsigned)min((long long)148 * 4, (total_q + 255) / 256);
         splitk_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(splitk_ws, p.split_stride, p.ksplit, bias, residual, y, total_q, Cout / 4);
         SGAM_LAUNCH_OK();

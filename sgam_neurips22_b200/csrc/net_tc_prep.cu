@@ -245,6 +245,18 @@ extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const fl
     return SGAM_OK;
 }
 
+extern "C" int sgam_groupnorm_split_apply(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
+                                          const double *partial, int B, long long HW, int C, int swish, void *stream) {
+    SGAM_REQUIRE(x && gamma && beta && hi && lo && partial, "groupnorm_split_apply: null pointer");
+    SGAM_REQUIRE(B > 0 && HW > 0 && C % 128 == 0 && C <= 1024, "groupnorm_split_apply: C=%d must be a multiple of 128 (<= 1024)", C);
+    const long long total = HW * (C / 8);
+    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
+    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, (cudaStream_t)stream>>>(x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
+                                                                             sgam_gn_splits(HW), swish);
+    SGAM_LAUNCH_OK();
+    return SGAM_OK;
+}
+
 extern "C" long long sgam_tc_gn_partial_floats(int B, int Ho, int Wo) {
     const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
     const long long tiles = (long long)cdiv(Wo, BW) * cdiv(Ho, BH);

@@ -370,6 +370,11 @@ def groupnorm_split(x, gamma, beta, swish, workspace=None):
                                                   partial.data_ptr(), B, x.shape[1], x.shape[2], C, int(swish), _stream()),
                    "sgam_groupnorm_split_fused")
         return hi, lo
+    partial64 = getattr(x, "gn_partial64", None)
+    if partial64 is not None:
+        _lib.check(lib.sgam_groupnorm_split_apply(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+                                                  partial64.data_ptr(), B, HW, C, int(swish), _stream()), "sgam_groupnorm_split_apply")
+        return hi, lo
     if workspace is None:
         workspace = torch.empty(B * lib.sgam_gn_splits(HW) * 64, dtype=torch.float64, device=x.device)
     _lib.check(lib.sgam_groupnorm_split(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), hi.data_ptr(), lo.data_ptr(),
@@ -411,18 +416,22 @@ def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=
     pair = _bf16_pair((B, Ho, Wo, Cout), x_hi.device) if out_split else (None, None)
     if residual is not None:
         _chk(residual, name="residual")
-    partial = splitk = None
+    partial = splitk = partial64 = None
     if out_f32 and not out_split and not out_nchw and Cout % 32 == 0:
         n_ws = lib.sgam_conv2d_tc_splitk_floats(B, H, W, Cin, Cout, ksize, stride)
-        if n_ws > 0:                    # under-filled grid: split the K loop (statistics then come from the stats kernel)
+        if n_ws > 0:                    # under-filled grid: split the K loop; the reduce kernel also takes the statistics
             splitk = torch.empty(n_ws, device=x_hi.device)
+            if gn_stats and Cout % 128 == 0 and Cout <= 1024:
+                partial64 = torch.empty(B * lib.sgam_gn_splits(Ho * Wo) * 64, dtype=torch.float64, device=x_hi.device)
     if splitk is None and gn_stats and out_f32 and not out_nchw and Cout % 128 == 0 and Cout <= 512:
         partial = torch.empty(lib.sgam_tc_gn_partial_floats(B, Ho, Wo), device=x_hi.device)
     _lib.check(lib.sgam_conv2d_tc(x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), _ptr(bias),
                                   _ptr(residual), _ptr(y), _ptr(pair[0]), _ptr(pair[1]), B, H, W, Cin, Cout, ksize,
-                                  stride, int(out_nchw), nsplit, _ptr(partial), _ptr(splitk), _stream()), "sgam_conv2d_tc")
+                                  stride, int(out_nchw), nsplit, _ptr(partial), _ptr(splitk), _ptr(partial64), _stream()), "sgam_conv2d_tc")
     if partial is not None:
         y.gn_partial = partial          # GroupNorm statistics of y, fused into the epilogue (consumed by groupnorm_split)
+    if partial64 is not None:
+        y.gn_partial64 = partial64      # ... or into the split-K reduction
     if out_f32 and out_split:
         return y, pair
     return y if out_f32 else pair
