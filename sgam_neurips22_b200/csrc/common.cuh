@@ -51,3 +51,49 @@ __device__ __forceinline__ float dot3(const float *a, float x0, float x1, float 
     t = __fmaf_rn(a[2], x2, t);
     return t;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A frame is ~300 dependent kernels, many of them a few microseconds long, so
+// the launch / dependency-resolution latency between consecutive kernels is a visible share of a single-trajectory
+// step.  Kernels launched through sgam_launch_pdl carry cudaLaunchAttributeProgrammaticStreamSerialization: the
+// front end may start scheduling their CTAs as soon as every CTA of the preceding kernel has executed
+// griddepcontrol.launch_dependents (or exited).  Every such kernel begins with SGAM_PDL_PROLOGUE() --
+// launch_dependents, then griddepcontrol.wait, which blocks until the preceding grid has COMPLETED and its memory is
+// visible -- before it touches global memory, so the data dependences are exactly those of plain stream order (also
+// when captured into a CUDA graph, where the edge becomes a programmatic dependency).  SGAM_PDL=0 launches them as
+// ordinary kernels (the two instructions are then no-ops); SGAM_PDL=<mask> enables it per kernel family.
+// STATUS (round 1): EXPERIMENTAL, default mask 0.  Measured on B200 (profiles/r1_pdl_experiment.txt): GEMM families
+// only (mask 3) +5 % single-trajectory frames/s, +1 % at 8 trajectories, all parity tests green; elementwise families
+// only (mask 28) no gain; GEMMs + softmax (mask 11) HANGS at 512x512 (softmax_split_kernel<8>, 16384 CTAs of 87
+// registers, as the dependent of the 2-CTA QK^T GEMM) although every kernel waits before touching memory -- not
+// understood yet, so nothing is enabled by default.
+#ifdef __CUDACC__
+#define SGAM_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define SGAM_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define SGAM_PDL_PROLOGUE() \
+    do {                    \
+        SGAM_PDL_TRIGGER(); \
+        SGAM_PDL_WAIT();    \
+    } while (0)
+
+bool sgam_pdl_enabled(int family);
+enum { SGAM_PDL_GEMM1 = 1, SGAM_PDL_GEMM2 = 2, SGAM_PDL_NORM = 4, SGAM_PDL_SOFTMAX = 8, SGAM_PDL_MISC = 16 };
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sgam_launch_pdl(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = sgam_pdl_enabled(family) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// kernel<<<grid, block, smem, stream>>>(args...) + SGAM_LAUNCH_OK(), as a PDL launch; parenthesise template-ids with commas
+#define SGAM_PDL_LAUNCH(family, kernel, grid, block, smem, stream, ...)                                          \
+    do {                                                                                                 \
+        ++g_sgam_launches;                                                                               \
+        SGAM_CUDA_OK(sgam_launch_pdl(family, kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)); \
+    } while (0)
+#endif

@@ -288,6 +288,7 @@ conv3x3_head_kernel(const float *__restrict__ x, const float *__restrict__ w, co
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float *__restrict__ x, double *__restrict__ partial, long long HW, int C, int S) {
+    SGAM_PDL_PROLOGUE();
     __shared__ double red[256][2];
     const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
     const int CQ = C / 4, PL = 256 / CQ, cq = tid % CQ, pl = tid / CQ;
@@ -398,8 +399,7 @@ softmax_rows_kernel(float *__restrict__ x, int cols) {
 // shared with net_tc.cu (GroupNorm statistics are the same kernel on both paths)
 int sgam_gn_stats_launch(const float *x, double *partial, int B, long long HW, int C, cudaStream_t s) {
     const int S = sgam_gn_splits(HW);
-    gn_stats_kernel<<<dim3(S, B), 256, 0, s>>>(x, partial, HW, C, S);
-    SGAM_LAUNCH_OK();
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_stats_kernel, dim3(S, B), 256, 0, s, x, partial, HW, C, S);
     return SGAM_OK;
 }
 

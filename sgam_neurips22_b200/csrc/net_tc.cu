@@ -47,6 +47,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams p) {
     using Cfg = TcCfg<BN, BK, STAGES, MT>;
     constexpr int ROW_BYTES = Cfg::ROW_BYTES, A_PLANE = Cfg::A_PLANE, B_PLANE = Cfg::B_PLANE, STAGE_BYTES = Cfg::STAGE_BYTES;
+    SGAM_PDL_TRIGGER();                              // the next kernel may start launching; it waits for our completion itself
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // swizzle atoms need 1024-B alignment
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
@@ -71,6 +72,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    SGAM_PDL_WAIT();                                 // barriers / TMEM are set up; operands of the preceding kernel from here on
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -233,6 +235,7 @@ TilePlan plan_tiles(int B, int Ho, int Wo, int N) {
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float *__restrict__ ws, long long split_stride, int ksplit, const float *__restrict__ bias,
                      const float *__restrict__ R, float *__restrict__ D, long long total_q, int NQ) {
+    SGAM_PDL_PROLOGUE();
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_q; e += (long long)gridDim.x * blockDim.x) {
         float4 a = __ldg(reinterpret_cast<const float4 *>(ws) + e);
         for (int s = 1; s < ksplit; ++s) {
@@ -258,6 +261,7 @@ splitk_reduce_kernel(const float *__restrict__ ws, long long split_stride, int k
 __global__ void __launch_bounds__(256)
 splitk_reduce_stats_kernel(const float *__restrict__ ws, long long split_stride, int ksplit, const float *__restrict__ bias,
                            const float *__restrict__ R, float *__restrict__ D, double *__restrict__ partial, long long HW, int C, int S) {
+    SGAM_PDL_PROLOGUE();
     __shared__ double red[256][2];
     const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
     const int CQ = C / 4, PL = 256 / CQ, cq = tid % CQ, pl = tid / CQ;
@@ -319,8 +323,7 @@ int launch_cfg(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorM
     }
     const int total = p.tiles_m * p.tiles_n * p.ksplit;
     const int grid = total < sm_count_cached() ? total : sm_count_cached();      // persistent: one CTA per SM
-    tc_gemm_kernel<BN, BK, STAGES, MT><<<grid, TC_THREADS, Cfg::SMEM, s>>>(a_hi, a_lo, b_hi, b_lo, p);
-    SGAM_LAUNCH_OK();
+    SGAM_PDL_LAUNCH(SGAM_PDL_GEMM1, (tc_gemm_kernel<BN, BK, STAGES, MT>), grid, TC_THREADS, Cfg::SMEM, s, a_hi, a_lo, b_hi, b_lo, p);
     return SGAM_OK;
 }
 
@@ -415,14 +418,12 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
         if (splitk_gn_partial && Cout % 128 == 0 && Cout <= 1024) {          // reduction + GroupNorm statistics in one pass
             const long long HW = (long long)Ho * Wo;
             const int S = sgam_gn_splits(HW);
-            splitk_reduce_stats_kernel<<<dim3(S, B), 256, 0, (cudaStream_t)stream>>>(splitk_ws, p.split_stride, p.ksplit, bias, residual, y,
+            SGAM_PDL_LAUNCH(SGAM_PDL_MISC, splitk_reduce_stats_kernel, dim3(S, B), 256, 0, (cudaStream_t)stream, splitk_ws, p.split_stride, p.ksplit, bias, residual, y,
                                                                                      splitk_gn_partial, HW, Cout, S);
-            SGAM_LAUNCH_OK();
             return SGAM_OK;
         }
         const unsigned blocks = (unsigned)min((long long)148 * 4, (total_q + 255) / 256);
-        splitk_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(splitk_ws, p.split_stride, p.ksplit, bias, residual, y, total_q, Cout / 4);
-        SGAM_LAUNCH_OK();
+        SGAM_PDL_LAUNCH(SGAM_PDL_MISC, splitk_reduce_kernel, blocks, 256, 0, (cudaStream_t)stream, splitk_ws, p.split_stride, p.ksplit, bias, residual, y, total_q, Cout / 4);
         return SGAM_OK;
     }
     return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, (cudaStream_t)stream);

@@ -89,6 +89,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                 const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams p, const Pair g) {
     using Cfg = Tc2Cfg<BN, STAGES>;
     constexpr int A_PLANE = Cfg::A_PLANE, B_PLANE = Cfg::B_PLANE, STAGE_BYTES = Cfg::STAGE_BYTES, BK = 64;
+    SGAM_PDL_TRIGGER();                              // the next kernel may start launching; it waits for our completion itself
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
@@ -116,6 +117,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     cluster_sync_all();                                          // barriers initialised and TMEM allocated in both CTAs
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    SGAM_PDL_WAIT();                                 // barriers / TMEM are set up; operands of the preceding kernel from here on
 
     if (warp == 0) {
         // ===== TMA producer (one thread per CTA): own A rows, own half of B; completion lands on the leader's barrier =====
@@ -220,8 +222,7 @@ int launch2_cfg(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensor
     }
     const int total = p.tiles_m * p.tiles_n, max_clusters = sm_count_cached() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
-    tc_gemm2_kernel<BN, STAGES><<<2 * clusters, TC_THREADS, Cfg::SMEM, s>>>(a_hi, a_lo, b_hi, b_lo, p, g);
-    SGAM_LAUNCH_OK();
+    SGAM_PDL_LAUNCH(SGAM_PDL_GEMM2, (tc_gemm2_kernel<BN, STAGES>), 2 * clusters, TC_THREADS, Cfg::SMEM, s, a_hi, a_lo, b_hi, b_lo, p, g);
     return SGAM_OK;
 }
 

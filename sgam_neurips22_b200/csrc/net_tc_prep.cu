@@ -13,6 +13,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
                   long long total_o, int H, int W, int CO, int up) {
+    SGAM_PDL_PROLOGUE();
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total_o; e += (long long)gridDim.x * blockDim.x) {
         long long src = e;
         if (up) {
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256)
 gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ meanrstd,
                       const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ hi,
                       __nv_bfloat16 *__restrict__ lo, long long HW, int C, int S, int swish) {
+    SGAM_PDL_PROLOGUE();
     __shared__ float mean_s[32], rstd_s[32];
     const int b = blockIdx.y, tid = threadIdx.x;
     if (meanrstd) {                     // statistics already finalised (fused into the producing conv's epilogue)
@@ -86,6 +88,7 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
 template <int VPT>
 __global__ void __launch_bounds__(256)
 softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cols) {
+    SGAM_PDL_PROLOGUE();
     __shared__ float sh[8];
     const float *row = x + (size_t)blockIdx.x * cols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = cols / 8;
@@ -161,6 +164,7 @@ softmax_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi
 __global__ void __launch_bounds__(256)
 stem_split_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask, const float *__restrict__ w,
                   const float *__restrict__ bias, int HW, int CP, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+    SGAM_PDL_PROLOGUE();
     const int p = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (p >= HW) return;
     float in[5];
@@ -188,6 +192,7 @@ stem_split_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask,
 // reduce the per-pixel-block partial sums written by tc_gemm_kernel's epilogue: [B][tiles][32][2] fp32 -> mean, rstd
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrstd, int tiles, double count) {
+    SGAM_PDL_PROLOGUE();
     __shared__ double red[8][32][2];
     const int b = blockIdx.x, g = threadIdx.x & 31, w = threadIdx.x >> 5;
     double a = 0.0, q = 0.0;
@@ -216,7 +221,7 @@ extern "C" int sgam_stem_conv_split(const float *x, const uint8_t *mask, const f
                                     int Cpad, void *hi, void *lo, void *stream) {
     SGAM_REQUIRE(x && w && bias && hi && lo && B > 0 && H > 0 && W > 0 && Cpad >= 8 && Cpad % 8 == 0, "stem_conv_split: bad arguments");
     dim3 grid(cdiv((long long)H * W, 256), B);
-    stem_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mask, w, bias, H * W, Cpad, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo);
+    SGAM_CUDA_OK(sgam_launch_pdl(SGAM_PDL_MISC, stem_split_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, mask, w, bias, H * W, Cpad, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo));
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
@@ -225,8 +230,7 @@ extern "C" int sgam_split_bf16(const float *x, void *hi, void *lo, int B, int H,
     SGAM_REQUIRE(x && hi && lo && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "split_bf16: C must be a multiple of 8");
     const long long total_o = (long long)B * (H << upsample) * (W << upsample) * (C / 8);
     const unsigned blocks = (unsigned)min((long long)148 * 16, (total_o + 255) / 256);
-    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, total_o, H, W, C / 8, upsample);
-    SGAM_LAUNCH_OK();
+    SGAM_PDL_LAUNCH(SGAM_PDL_MISC, split_bf16_kernel, blocks, 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, total_o, H, W, C / 8, upsample);
     return SGAM_OK;
 }
 
@@ -239,9 +243,8 @@ extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const fl
     if (rc) return rc;
     const long long total = HW * (C / 8);
     const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
-    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
                                                           sgam_gn_splits(HW), swish);
-    SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
 
@@ -251,9 +254,8 @@ extern "C" int sgam_groupnorm_split_apply(const float *x, const float *gamma, co
     SGAM_REQUIRE(B > 0 && HW > 0 && C % 128 == 0 && C <= 1024, "groupnorm_split_apply: C=%d must be a multiple of 128 (<= 1024)", C);
     const long long total = HW * (C / 8);
     const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
-    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, (cudaStream_t)stream>>>(x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, (cudaStream_t)stream, x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
                                                                              sgam_gn_splits(HW), swish);
-    SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
 
@@ -272,12 +274,10 @@ extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, co
     const int tiles = cdiv(Wo, BW) * cdiv(Ho, BH);
     const long long HW = (long long)Ho * Wo;
     float *meanrstd = gn_partial + (long long)B * tiles * 64;
-    gn_finalize_kernel<<<B, 256, 0, s>>>(gn_partial, meanrstd, tiles, (double)HW * (C / 32));
-    SGAM_LAUNCH_OK();
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_finalize_kernel, B, 256, 0, s, gn_partial, meanrstd, tiles, (double)HW * (C / 32));
     const long long total = HW * (C / 8);
     const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
-    gn_apply_split_kernel<<<dim3(blocks, B), 256, 0, s>>>(x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
-    SGAM_LAUNCH_OK();
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
     return SGAM_OK;
 }
 
@@ -285,11 +285,10 @@ extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long 
     SGAM_REQUIRE(x && hi && lo && rows > 0 && cols > 0 && cols % 8 == 0, "softmax_split: cols must be a multiple of 8");
     cudaStream_t s = (cudaStream_t)stream;
     __nv_bfloat16 *h = (__nv_bfloat16 *)hi, *l = (__nv_bfloat16 *)lo;
-    if (cols <= 2048) softmax_split_kernel<1><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else if (cols <= 4096) softmax_split_kernel<2><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else if (cols <= 16384) softmax_split_kernel<8><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    else softmax_split_kernel<0><<<(unsigned)rows, 256, 0, s>>>(x, h, l, cols);
-    SGAM_LAUNCH_OK();
+    if (cols <= 2048) SGAM_PDL_LAUNCH(SGAM_PDL_SOFTMAX, softmax_split_kernel<1>, (unsigned)rows, 256, 0, s, x, h, l, cols);
+    else if (cols <= 4096) SGAM_PDL_LAUNCH(SGAM_PDL_SOFTMAX, softmax_split_kernel<2>, (unsigned)rows, 256, 0, s, x, h, l, cols);
+    else if (cols <= 16384) SGAM_PDL_LAUNCH(SGAM_PDL_SOFTMAX, softmax_split_kernel<8>, (unsigned)rows, 256, 0, s, x, h, l, cols);
+    else SGAM_PDL_LAUNCH(SGAM_PDL_SOFTMAX, softmax_split_kernel<0>, (unsigned)rows, 256, 0, s, x, h, l, cols);
     return SGAM_OK;
 }
 
