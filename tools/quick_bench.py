@@ -1,10 +1,9 @@
 """Per-stage device timings of one scene-generation step (development aid; the judged numbers come from bench.py)."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle import recipes, model as omodel
-from sgam_neurips22_b200 import ops
-from sgam_neurips22_b200.vqgan import VQGANEngine
+from sgam_neurips22_b200 import ops, synthetic
+from sgam_neurips22_b200.model import VQModel
 
 def timeit(fn, n=5, warm=2):
     for _ in range(warm): fn()
@@ -17,15 +16,17 @@ def timeit(fn, n=5, warm=2):
 
 ds = sys.argv[1] if len(sys.argv) > 1 else "clevr-infinite"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-sd = recipes.make_state_dict(recipes.DATASETS[ds]["n_embed"], 0)
-eng = VQGANEngine(sd, recipes.DDCONFIG)
-batch = recipes.scene_step_inputs(ds, 61, res=256, batch=B)
-Ks = batch["Ks"]; Kinv = torch.from_numpy(Ks.reshape(-1,3,3)).inverse().numpy().reshape(Ks.shape)
-T = omodel.src2tgt_transforms(batch["R_rels"], batch["t_rels"])
-d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-rgb, dep, Kt, Ki, Tt = d(batch["src_imgs"]), d(batch["src_depths"]), d(Ks[:,0]), d(Kinv), d(T)
-g = ops.splat_forward(rgb, dep, Kt, Ki, Tt, ds, channels_last=True)
-print("splat ms", timeit(lambda: ops.splat_forward(rgb, dep, Kt, Ki, Tt, ds, channels_last=True), 20))
+model = synthetic.randomize_weights(VQModel(**synthetic.model_kwargs(ds)), seed=0).to("cuda:0").eval()
+eng = model.engine
+batch = synthetic.scene_step_batch(ds, res=256, batch=B, seed=61)
+host = {k: torch.from_numpy(v) for k, v in batch.items()}
+N = host["src_depths"].shape[1]
+Kinv, K_tgt = model._kinv(host["Ks"]), host["Ks"][:, 0].contiguous().cuda()
+T = torch.eye(4).repeat(B, N, 1, 1)
+T[..., :3, :3], T[..., :3, 3] = host["R_rels"], host["t_rels"]
+rgb, dep, Tt = host["src_imgs"].cuda(), host["src_depths"].cuda(), T.cuda()
+g = ops.splat_forward(rgb, dep, K_tgt, Kinv, Tt, ds, channels_last=True)
+print("splat ms", timeit(lambda: ops.splat_forward(rgb, dep, K_tgt, Kinv, Tt, ds, channels_last=True), 20))
 x, m = g["x"], g["mask"]
 pre = eng.encode(x, m)
 print("encode ms", timeit(lambda: eng.encode(x, m)))
