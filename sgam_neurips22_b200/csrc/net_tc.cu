@@ -201,20 +201,28 @@ struct TilePlan {
 
 // Column-tile width: 128 unless the grid would leave most of the SMs idle, in which case 64-wide tiles double the
 // tile count (tcgen05 runs N = 64 at the same MAC rate).  Cost model: waves * (BN + fixed per-tile overhead).
-int pick_bn(long long tiles_m, int N) {
+int pick_bn(long long tiles_m, int N, int num_kb) {
     if (N % 64) return 32;
     if (N % 128) return 64;
     const int sms = sm_count_cached();
+    // Long-K layers with a quarter to half a wave of 128-wide tiles (the 512-channel 16x16 convs at 8 trajectories):
+    // 64-wide tiles fill the machine but every CTA then pulls a full-K slab of A for 64 columns and the layer is bound
+    // by L2 -> SMEM bandwidth (ncu: 453 MB per launch at 9.6 TB/s, tensor pipe 35 %).  128-wide tiles with a 2-way
+    // split-K launch as many CTAs and move a third less.
+    if (num_kb >= 16) {
+        const long long t = tiles_m * (N / 128);
+        if (2 * t <= sms && 4 * t > sms) return 128;
+    }
     const long long t128 = tiles_m * (N / 128), t64 = tiles_m * (N / 64);
     const long long c128 = ((t128 + sms - 1) / sms) * (128 + 32), c64 = ((t64 + sms - 1) / sms) * (64 + 32);
     return c64 < c128 ? 64 : 128;
 }
 
-TilePlan plan_tiles(int B, int Ho, int Wo, int N) {
+TilePlan plan_tiles(int B, int Ho, int Wo, int N, int num_kb = 0) {
     TilePlan t;
     const int BW1 = Wo >= 128 ? 128 : Wo, BH1 = 128 / BW1;
     const long long tiles1 = (long long)cdiv(Wo, BW1) * cdiv(Ho, BH1) * B;
-    t.BN = pick_bn(tiles1, N);
+    t.BN = pick_bn(tiles1, N, num_kb);
     t.BK = 64; t.MT = 1; t.BW = BW1; t.BH = BH1;
     const int v = tc_variant();
     if (v == 3) {
@@ -387,7 +395,7 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
         p.stats = gn_partial; p.cpg = Cout / 32;
         return launch_tc2(BN2, a_hi, a_lo, b_hi, b_lo, p, B, Ho, Wo, Npad, (cudaStream_t)stream);
     }
-    TilePlan t = plan_tiles(B, Ho, Wo, Npad);
+    TilePlan t = plan_tiles(B, Ho, Wo, Npad, (splitk_ws && !gn_partial) ? ksize * ksize * (Cin / 64) : 0);
     if (stride == 2 && t.MT == 2) { t.MT = 1; t.BW = Wo >= 128 ? 128 : Wo; t.BH = 128 / t.BW; }   // TMA box extent <= 256 elements
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     const long long adims[4] = {Cin, W, H, B};
@@ -434,7 +442,7 @@ extern "C" long long sgam_conv2d_tc_splitk_floats(int B, int H, int W, int Cin, 
     if (stride != 1 && stride != 2) return 0;
     const int Ho = H / stride, Wo = W / stride;
     if (Ho <= 0 || Wo <= 0 || !sgam_tc_supported_conv(Ho, Wo, Cin, Cout, ksize, stride) || Cout % 32) return 0;
-    TilePlan t = plan_tiles(B, Ho, Wo, Cout);
+    TilePlan t = plan_tiles(B, Ho, Wo, Cout, ksize * ksize * (Cin / 64));
     if (stride == 2 && t.MT == 2) { t.MT = 1; t.BW = Wo >= 128 ? 128 : Wo; t.BH = 128 / t.BW; }
     const long long tiles = (long long)cdiv(Wo, t.BW) * cdiv(Ho, t.BH) * B * cdiv(Cout, t.BN);
     const int num_kb = ksize * ksize * (Cin / t.BK);
