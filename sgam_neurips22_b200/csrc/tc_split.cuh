@@ -3,10 +3,13 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+// hi = bf16(x) (round to nearest even), lo = bf16(x - hi); element a in the low half-word, b in the high one.
+// One packed conversion per pair (cvt.rn.bf16x2.f32 -> F2FP.BF16.F32.PACK_AB) and integer re-expansion of hi: 6
+// instructions per pair instead of 10 with scalar conversions + byte permutes; the results are bit-identical.
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0)), l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
 }
-
