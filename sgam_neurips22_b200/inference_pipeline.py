@@ -71,7 +71,7 @@ def forward_splat_depth(pipe, src_nodes, T_tgt):
         T_src[:3, :3], T_src[:3, 3] = n["R"], n["t"]
         T[0, i] = torch.from_numpy((T_tgt @ np.linalg.inv(T_src)).astype(np.float32))
     Kinv = K.inverse()[None, None].repeat(1, N, 1, 1).contiguous()
-    out = ops.splat_forward(rgb, dm, K[None].to(dev), Kinv.to(dev), T.to(dev), pipe.data, channels_last=True,
+    out = ops.splat_forward(rgb, dm, ops.h2d(K[None], dev), ops.h2d(Kinv, dev), ops.h2d(T, dev), pipe.data, channels_last=True,
                             policy=ops.SPLAT_ZMIN, want_merge_depth=True)
     return out["merge_depth"][0, 0]
 
@@ -306,7 +306,7 @@ class InfiniteSceneGeneration:
         rgb = src_imgs.permute(0, 1, 3, 4, 2) if channels_last else src_imgs.contiguous()
         out = ops.inverse_warp(rgb, torch.as_tensor(src_depths).to(dev, torch.float32).contiguous(),
                                torch.as_tensor(tgt_depth).to(dev, torch.float32).contiguous(),
-                               Kinv_tgt.to(dev).contiguous(), proj.to(dev).contiguous(), channels_last=channels_last)
+                               ops.h2d(Kinv_tgt, dev), ops.h2d(proj, dev), channels_last=channels_last)
         return out[0].cpu().numpy() if as_numpy else out[0]
 
     def _init_volume(self):

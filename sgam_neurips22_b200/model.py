@@ -179,7 +179,7 @@ class VQModel(torch.nn.Module):
         if hit is None or hit.device != self.device:
             if len(self._kinv_cache) > 64:
                 self._kinv_cache.clear()
-            hit = Kh.reshape(-1, 3, 3).inverse().reshape(Kh.shape).contiguous().to(self.device)
+            hit = ops.h2d(Kh.reshape(-1, 3, 3).inverse().reshape(Kh.shape), self.device)
             self._kinv_cache[key] = hit
         return hit
 
@@ -204,14 +204,14 @@ class VQModel(torch.nn.Module):
             Ks = batch["Ks"]
             Ks_host = Ks if (torch.is_tensor(Ks) and not Ks.is_cuda) else torch.as_tensor(Ks).cpu()
             Kinv = self._kinv(Ks_host)
-            K_tgt = f32(Ks_host[:, 0]).contiguous()
+            K_tgt = ops.h2d(Ks_host[:, 0], dev, torch.float32)
             R = torch.as_tensor(batch["R_rels"]).detach().to("cpu", torch.float32)
             t = torch.as_tensor(batch["t_rels"]).detach().to("cpu", torch.float32)
             T = torch.eye(4).repeat(B, N, 1, 1)                                  # model.py:188-195
             T[..., :3, :3] = R
             T[..., :3, 3] = t
             channels_last = src.shape[-1] == 3 and src.dim() == 5 and src.shape[2] != 3
-            out = ops.splat_forward(src.contiguous(), dm.contiguous(), K_tgt, Kinv, T.to(dev), dataset,
+            out = ops.splat_forward(src.contiguous(), dm.contiguous(), K_tgt, Kinv, ops.h2d(T, dev), dataset,
                                     channels_last=channels_last, policy=self.splat_policy)
             x, mask = out["x"], out["mask"]
         extrapolation_mask = mask.view(torch.bool)

@@ -30,6 +30,19 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def h2d(t, device, dtype=None):
+    """Upload a small host tensor (intrinsics, poses) WITHOUT stalling the host: `.to(device)` from pageable memory is a
+    cudaMemcpyAsync + stream synchronize, i.e. the host waits for every kernel already queued, which serialises the scene
+    loop's host work with the previous frame's GPU work.  Staging through the caching pinned allocator keeps the copy
+    asynchronous and stream ordered (the allocator holds the pinned block until the copy has run)."""
+    t = torch.as_tensor(t)
+    if dtype is not None:
+        t = t.to(dtype)
+    if t.is_cuda:
+        return t.to(device)
+    return t.contiguous().pin_memory().to(device, non_blocking=True)
+
+
 def dataset_id(dataset):
     if dataset not in DATASET_ID:
         raise NotImplementedError(dataset)        # same error the reference raises (model.py:230-231)
@@ -122,7 +135,7 @@ def unproject_points(depth, rgb_u8, K, Rt):
         _chk(rgb_u8, torch.uint8, "rgb_u8")
     Kinv = np.ascontiguousarray(np.linalg.inv(np.asarray(K, np.float64)))
     Rt = np.asarray(Rt, np.float64).reshape(F, 4, 4)
-    Rt_inv = torch.from_numpy(np.ascontiguousarray(np.stack([np.linalg.inv(m)[:3] for m in Rt]))).to(depth.device)
+    Rt_inv = h2d(torch.from_numpy(np.ascontiguousarray(np.stack([np.linalg.inv(m)[:3] for m in Rt]))), depth.device)
     xyz = torch.empty(F * H * W, 3, dtype=torch.float64, device=depth.device)
     col = torch.empty(F * H * W, 3, dtype=torch.float64, device=depth.device) if rgb_u8 is not None else None
     for f0 in range(0, F, 65535):                                           # frames ride in grid.y
