@@ -139,3 +139,16 @@ def test_scene_loop_with_rgbd_integration_runs_on_the_device_volume(tmp_path, mo
     assert np.array_equal(pipe.volume.vol.cpu().numpy(), ref.vol)
     pts, cols = pipe.volume.extract_point_cloud()
     assert len(pts) > 1000 and float(cols.min()) >= 0.0 and float(cols.max()) <= 1.0 + 1e-6
+
+
+def test_empty_frame_and_empty_cloud():
+    """Edge case: a frame without valid depth opens no unit; ray cast and cloud extraction return nothing."""
+    from sgam_neurips22_b200.tsdf import TSDFVolume
+    dev = TSDFVolume(0.01, 0.03, [-0.5, -0.5, 1.5], [0.5, 0.5, 2.5], with_color=False)
+    d = torch.zeros(H, W, device="cuda")
+    d[:8] = 40.0                                                         # beyond depth_trunc: ignored as well
+    dev.integrate(d, None, K, np.eye(4))
+    assert int(dev.stamp.abs().sum()) == 0 and float(dev.vol.abs().sum()) == 0.0
+    assert float(dev.render_depth(K, np.eye(4), H, W, z_far=4.0).abs().sum()) == 0.0
+    xyz, col = dev.extract_point_cloud()
+    assert tuple(xyz.shape) == (0, 3) and tuple(col.shape) == (0, 3)

@@ -160,3 +160,23 @@ def test_unproject_records_matches_prepare_pcd():
         ref = native.unproject_world(depth[f], np.linalg.inv(K), np.linalg.inv(Rt))
         assert np.allclose(xyz[f * 42:(f + 1) * 42].numpy(), ref, atol=1e-9)
     assert np.allclose(col.numpy(), rgb.reshape(-1, 3) / 255.0)
+
+
+def test_frustum_box_contains_every_point_the_cameras_can_see():
+    from sgam_neurips22_b200.tsdf import frustum_box
+    rng = np.random.default_rng(3)
+    K = np.array([[248.88887, 0, 128], [0, 248.88887, 128], [0, 0, 1.0]])
+    poses = []
+    for i in range(5):
+        c, s = np.cos(0.5), np.sin(0.5)
+        c2w = np.eye(4)
+        c2w[:3, :3] = np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+        c2w[:3, 3] = [-3.0, -6.0 + 0.06 * i, 2.0]
+        poses.append(np.linalg.inv(c2w @ np.diag([1., -1., -1., 1.])))
+    lo, hi = frustum_box(K, poses, 256, 256, z_far=5.0, pad=0.1)
+    for T in poses:
+        uv = rng.uniform(0, 256, (200, 2))
+        z = rng.uniform(0.05, 5.0, 200)
+        cam = np.stack([(uv[:, 0] - 128) / K[0, 0] * z, (uv[:, 1] - 128) / K[1, 1] * z, z, np.ones(200)])
+        world = (np.linalg.inv(T) @ cam)[:3]
+        assert (world.min(1) >= lo).all() and (world.max(1) <= hi).all()

@@ -104,3 +104,19 @@ def test_tilted_plane_depth_error_is_sub_voxel():
     assert (out[inner] > 0).mean() > 0.99
     err = np.abs(out[inner] - depth[inner])[out[inner] > 0]
     assert err.max() < 1.0 * vox and err.mean() < 0.3 * vox
+
+
+def test_empty_frame_opens_nothing_and_renders_nothing():
+    vol = make_volume()
+    vol.integrate(np.zeros((H, W), np.float32), None, K4, np.eye(4))
+    assert not vol.stamp.any() and not vol.vol.any()
+    assert not vol.render_depth(K4, np.eye(4), H, W, z_far=4.0).any()
+    xyz, col = vol.extract_point_cloud()
+    assert xyz.shape == (0, 3) and col.shape == (0, 3)
+
+
+def test_surface_outside_the_dense_box_is_dropped():
+    """Re-design (1): units outside the caller's box are ignored (Open3D's hash would allocate them)."""
+    vol = make_volume(z0=2.0)
+    vol.integrate(plane_depth(6.0), None, K4, np.eye(4))               # the plane lies far behind the box
+    assert not vol.stamp.any()
