@@ -189,26 +189,29 @@ stem_split_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask,
     for (int k = 1; k < CP / 8; ++k) { dh[k] = z; dl[k] = z; }
 }
 
-// reduce the per-pixel-block partial sums written by tc_gemm_kernel's epilogue: [B][tiles][32][2] fp32 -> mean, rstd
+// reduce the per-pixel-block partial sums written by the GEMM epilogue: [B][tiles][32][2] fp32 -> mean, rstd.
+// One WARP per (batch element, group): lane l adds tiles l, l + 32, ... in fp64, then a fixed butterfly combines the
+// lanes (deterministic).  256 warps for 8 trajectories instead of 8 CTAs walking 64 tiles per thread: the kernel is a
+// pure latency chain, so the shorter chain is what matters (7 us -> ~3 us, 48 launches per step).
 __global__ void __launch_bounds__(256)
-gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrstd, int tiles, double count) {
+gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrstd, int tiles, double count, int pairs) {
     SGAM_PDL_PROLOGUE();
-    __shared__ double red[8][32][2];
-    const int b = blockIdx.x, g = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, pair = blockIdx.x * 8 + (threadIdx.x >> 5);      // pair = b * 32 + g
+    if (pair >= pairs) return;
+    const int b = pair >> 5, g = pair & 31;
     double a = 0.0, q = 0.0;
-    for (int t = w; t < tiles; t += 8) {
-        const float2 v = *reinterpret_cast<const float2 *>(partial + (((size_t)b * tiles + t) * 32 + g) * 2);
+    for (int t = lane; t < tiles; t += 32) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(partial + (((size_t)b * tiles + t) * 32 + g) * 2));
         a += (double)v.x; q += (double)v.y;
     }
-    red[w][g][0] = a; red[w][g][1] = q;
-    __syncthreads();
-    if (w == 0) {
-        for (int k = 1; k < 8; ++k) { a += red[k][g][0]; q += red[k][g][1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
         const double mean = a / count;
         double var = q / count - mean * mean;
         var = var < 0.0 ? 0.0 : var;
-        meanrstd[(b * 32 + g) * 2] = (float)mean;
-        meanrstd[(b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-6));
+        meanrstd[pair * 2] = (float)mean;
+        meanrstd[pair * 2 + 1] = (float)(1.0 / sqrt(var + 1e-6));
     }
 }
 
@@ -274,7 +277,7 @@ extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, co
     const int tiles = cdiv(Wo, BW) * cdiv(Ho, BH);
     const long long HW = (long long)Ho * Wo;
     float *meanrstd = gn_partial + (long long)B * tiles * 64;
-    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_finalize_kernel, B, 256, 0, s, gn_partial, meanrstd, tiles, (double)HW * (C / 32));
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_finalize_kernel, cdiv(B * 32, 8), 256, 0, s, gn_partial, meanrstd, tiles, (double)HW * (C / 32), B * 32);
     const long long total = HW * (C / 8);
     const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
     SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
