@@ -180,3 +180,20 @@ def test_frustum_box_contains_every_point_the_cameras_can_see():
         cam = np.stack([(uv[:, 0] - 128) / K[0, 0] * z, (uv[:, 1] - 128) / K[1, 1] * z, z, np.ones(200)])
         world = (np.linalg.inv(T) @ cam)[:3]
         assert (world.min(1) >= lo).all() and (world.max(1) <= hi).all()
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The driver parses ONE JSON line from `bench.py --impl reference`; it runs the oracle port on the host cores only."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
