@@ -26,6 +26,7 @@ SOURCES = {
     "net_simt.cu": [],
     "net_tc.cu": [],
     "net_tc2.cu": [],
+    "net_tc3.cu": [],
     "net_tc_prep.cu": [],
 }
 

@@ -1,0 +1,261 @@
+// Stage (iii), 128-channel convolutions with SWAPPED operands (sm_100a).
+//
+// The 128 -> 128 channel 3x3 convolutions at 256x256 / 128x128 are 40 % of the network's tensor time, and with pixels
+// on the M side (tc_gemm_kernel / tc_gemm2_kernel) their MMA is 128 x 128 x 16: it reads 8 KB of operands from shared
+// memory in 64 clk = 128 B/clk, the SM's whole shared-memory bandwidth, so the tensor pipe idles at ~62 % while TMA
+// fills the ring (ncu).  The N = 256 GEMMs of the same network run at 84-92 %.  This kernel puts
+// the OUTPUT CHANNELS on the M side and 256 OUTPUT PIXELS on the N side,
+//
+//     D^T[c, p] = sum_k W[c, k] * A[p, k]        (c < 128 channels, p < 256 pixels of the tile)
+//
+// so the instruction is 128 x 256 x 16: 12 KB of operands per 128 clk = 96 B/clk.  Both operands are K-major swizzled
+// tiles exactly as before (the pixel tile is still ONE TMA box of the NHWC tensor shifted by the filter tap; only the
+// descriptor roles are exchanged), and the split-bf16 products are W_hi*A_hi + W_hi*A_lo + W_lo*A_hi.
+//
+// The accumulator arrives transposed -- TMEM lane = channel, column = pixel -- which suits the NHWC output: for a fixed
+// pixel the 32 lanes of a warp hold 32 consecutive channels, so every store (and residual load) of the epilogue is one
+// 128-byte line, no staging.  GroupNorm statistics: a group is 4 neighbouring lanes, each lane sums its channel over
+// the 128 pixels of a block in registers, two shuffles finish the group -- no shared memory, no cross-warp step.
+//
+// CTA = 6 warps as in tc_gemm_kernel (TMA producer, MMA issuer + TMEM allocation, 4 epilogue warps), persistent, two
+// 256-column accumulators in TMEM (all 512 columns) so that the epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdlib.h>
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace {
+
+using namespace tc;
+
+template <int BK, int STAGES>
+struct Tc3Cfg {
+    static constexpr int ROW_BYTES = BK * 2;
+    static constexpr int W_PLANE = 128 * ROW_BYTES;      // weight tile: 128 output channels (M side), one of (hi, lo)
+    static constexpr int P_PLANE = 256 * ROW_BYTES;      // pixel tile: 256 output pixels (N side)
+    static constexpr int STAGE_BYTES = 2 * W_PLANE + 2 * P_PLANE;
+    static constexpr int TMEM_COLS = 512;                // two 256-column fp32 accumulators
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
+    static_assert(SMEM <= 227 * 1024, "stage ring exceeds shared memory");
+};
+
+// 256-pixel boxes: BW2 x BH2 = 256 output pixels; the two 128-pixel halves of a box are the blocks the GroupNorm
+// partial-sum layout is defined on (sgam_tc_gn_partial_floats): neighbours in x when the image is >= 256 wide, in y otherwise
+struct SwapGeom {
+    int BW2, BH2, tiles_x2, tiles_y2, wide, tiles128_x, tiles128;
+};
+
+template <int BK, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_constant__ CUtensorMap mapP_lo,
+                    const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo, const TcParams p,
+                    const SwapGeom g) {
+    using Cfg = Tc3Cfg<BK, STAGES>;
+    constexpr int ROW_BYTES = Cfg::ROW_BYTES, W_PLANE = Cfg::W_PLANE, P_PLANE = Cfg::P_PLANE, STAGE_BYTES = Cfg::STAGE_BYTES;
+    SGAM_PDL_TRIGGER();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = p.taps * p.kblocks_per_tap;
+    const int total_tiles = p.tiles_m * p.tiles_n;          // pixel boxes x 128-channel tiles
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    SGAM_PDL_WAIT();
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (W_PLANE + P_PLANE);
+            int kbg = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.tiles_n) * 128;
+                int t = tile / p.tiles_n;
+                const int tx = t % g.tiles_x2; t /= g.tiles_x2;
+                const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
+                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+                    const int s = kbg % STAGES, it = kbg / STAGES;
+                    mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+                    uint8_t *st = smem + (size_t)s * STAGE_BYTES;
+                    const int tap = kb / p.kblocks_per_tap, kc = kb - tap * p.kblocks_per_tap;
+                    const int kh = tap / p.ks, kw = tap - kh * p.ks;
+                    const int cx = tx * g.BW2 + kw - p.pad, cy = ty * g.BH2 + kh - p.pad;
+                    mbar_expect_tx(&full_bar[s], tx_bytes);
+                    tma_load_3d(st, &mapW_hi, &full_bar[s], kb * BK, n0, 0);
+                    tma_load_4d(st + 2 * W_PLANE, &mapP_hi, &full_bar[s], kc * BK, cx, cy, b);
+                    if (p.nsplit == 3) {
+                        tma_load_3d(st + W_PLANE, &mapW_lo, &full_bar[s], kb * BK, n0, 0);
+                        tma_load_4d(st + 2 * W_PLANE + P_PLANE, &mapP_lo, &full_bar[s], kc * BK, cx, cy, b);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D^T (128 channels x 256 pixels) += W (128 x 16) . A^T (16 x 256) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 256);
+            int kbg = 0, li = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+                const int acc = li & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((li >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
+                    const int s = kbg % STAGES, it = kbg / STAGES;
+                    mbar_wait(&full_bar[s], it & 1);
+                    tc_fence_after();
+                    uint8_t *st = smem + (size_t)s * STAGE_BYTES;
+                    const uint64_t w_hi = make_smem_desc<ROW_BYTES>(st), w_lo = make_smem_desc<ROW_BYTES>(st + W_PLANE);
+                    const uint64_t a_hi = make_smem_desc<ROW_BYTES>(st + 2 * W_PLANE), a_lo = make_smem_desc<ROW_BYTES>(st + 2 * W_PLANE + P_PLANE);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t off = (uint64_t)(k * 2);
+                        umma_bf16(tmem_d, w_hi + off, a_hi + off, idesc, (kb || k) ? 1u : 0u);
+                        if (p.nsplit == 3) {
+                            umma_bf16(tmem_d, w_hi + off, a_lo + off, idesc, 1u);
+                            umma_bf16(tmem_d, w_lo + off, a_hi + off, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: warp q owns TMEM lanes 32q.. = output channels n0 + 32q + lane; columns are the box's pixels =====
+        const int q = warp & 3;
+        const int cpg = p.cpg;                                      // channels per GroupNorm group (4 for 128 channels)
+        int li = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+            const int acc = li & 1;
+            const int n0 = (tile % p.tiles_n) * 128;
+            int t = tile / p.tiles_n;
+            const int tx = t % g.tiles_x2; t /= g.tiles_x2;
+            const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
+            const int c = n0 + 32 * q + lane;                       // this thread's output channel
+            const float bn = p.bias_n ? __ldg(p.bias_n + c) : 0.0f;
+            mbar_wait(&tmem_full_bar[acc], (li >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+            float s_acc = 0.f, q_acc = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_acc + (uint32_t)c0, v);
+                const int ly = c0 / g.BW2, lx = c0 - ly * g.BW2;    // BW2 % 32 == 0: the 32 pixels of a chunk share a row
+                const long long m = (long long)(ty * g.BH2 + ly) * p.Wo + (tx * g.BW2 + lx);
+                const long long off = (long long)b * p.d_batch_stride + m * p.N + c;
+                float o[32];
+                if (p.R) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = __ldg(p.R + off + (long long)j * p.N);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] += p.alpha * __uint_as_float(v[j]) + bn;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bn;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) p.D[off + (long long)j * p.N] = o[j];       // lanes = 32 consecutive channels: one 128-byte line
+                if (p.stats) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { s_acc += o[j]; q_acc = fmaf(o[j], o[j], q_acc); }
+                    if ((c0 & 127) == 96) {                          // a 128-pixel block is complete
+                        float s = s_acc, qq = q_acc;
+                        for (int d = 1; d < cpg; d <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); qq += __shfl_xor_sync(0xffffffffu, qq, d); }
+                        if ((lane & (cpg - 1)) == 0) {
+                            const int half = c0 >> 7;
+                            const int tx128 = g.wide ? 2 * tx + half : tx, ty128 = g.wide ? ty : 2 * ty + half;
+                            const long long slot = (long long)b * g.tiles128 + (long long)ty128 * g.tiles128_x + tx128;
+                            const int grp = c / cpg;
+                            p.stats[(slot * 32 + grp) * 2] = s;
+                            p.stats[(slot * 32 + grp) * 2 + 1] = qq;
+                        }
+                        s_acc = 0.f; q_acc = 0.f;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+int swap_mode() {              // 0 = off, 64 = BK 64 / 2 stages, 32 = BK 32 / 4 stages (SGAM_TC_SWAP)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SGAM_TC_SWAP"); v = e ? atoi(e) : 64; if (v != 0 && v != 32 && v != 64) v = 64; }
+    return v;
+}
+
+template <int BK, int STAGES>
+int launch_swap(const CUtensorMap &p_hi, const CUtensorMap &p_lo, const CUtensorMap &w_hi, const CUtensorMap &w_lo, const TcParams &p,
+                const SwapGeom &g, cudaStream_t s) {
+    using Cfg = Tc3Cfg<BK, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_swap_kernel<BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int total = p.tiles_m * p.tiles_n;
+    const int grid = total < sm_count_cached() ? total : sm_count_cached();
+    SGAM_PDL_LAUNCH(SGAM_PDL_GEMM1, (tc_gemm_swap_kernel<BK, STAGES>), grid, TC_THREADS, Cfg::SMEM, s, p_hi, p_lo, w_hi, w_lo, p, g);
+    return SGAM_OK;
+}
+
+}  // namespace
+
+namespace tc {
+
+// Does the swapped-operand kernel apply?  128 output channels, stride 1, plain fp32 NHWC output, an image that tiles
+// exactly into 256-pixel boxes whose rows are a multiple of 32 pixels, and enough boxes to fill the machine.
+bool swap_applicable(int B, int Ho, int Wo, int Cin, int Cout, int stride, bool fp32_nhwc_only) {
+    if (!swap_mode() || Cout != 128 || stride != 1 || !fp32_nhwc_only || Cin % 64) return false;
+    const bool exact = (Wo >= 256) ? (Wo % 256 == 0) : (Wo >= 32 && (Wo & (Wo - 1)) == 0 && Ho % (256 / Wo) == 0);
+    if (!exact) return false;
+    return (long long)B * Ho * Wo / 256 >= sm_count_cached();
+}
+
+int launch_conv_swap(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, TcParams p, int B, int H, int W, int Cin,
+                     int Cout, int ksize, cudaStream_t s) {
+    const int mode = swap_mode(), BK = mode == 32 ? 32 : 64;
+    SwapGeom g;
+    g.BW2 = W >= 256 ? 256 : W; g.BH2 = 256 / g.BW2; g.tiles_x2 = W / g.BW2; g.tiles_y2 = H / g.BH2;
+    g.wide = W >= 256; g.tiles128_x = W >= 128 ? W / 128 : 1;
+    { const int BW = W >= 128 ? 128 : W, BH = 128 / BW; g.tiles128 = cdiv(W, BW) * cdiv(H, BH); }
+    CUtensorMap p_hi, p_lo, wm_hi, wm_lo;
+    const long long adims[4] = {Cin, W, H, B};
+    const int abox[4] = {BK, g.BW2, g.BH2, 1};
+    const long long bdims[3] = {(long long)ksize * ksize * Cin, Cout, 1};
+    const int bbox[3] = {BK, 128, 1};
+    int rc;
+    if ((rc = make_map(&p_hi, x_hi, 4, adims, abox)) || (rc = make_map(&p_lo, x_lo, 4, adims, abox)) ||
+        (rc = make_map(&wm_hi, w_hi, 3, bdims, bbox)) || (rc = make_map(&wm_lo, w_lo, 3, bdims, bbox)))
+        return rc;
+    p.kblocks_per_tap = Cin / BK;
+    p.tiles_m = g.tiles_x2 * g.tiles_y2 * B;
+    p.tiles_n = Cout / 128;
+    p.ksplit = 1;
+    if (BK == 32) return launch_swap<32, 4>(p_hi, p_lo, wm_hi, wm_lo, p, g, s);
+    return launch_swap<64, 2>(p_hi, p_lo, wm_hi, wm_lo, p, g, s);
+}
+
+}  // namespace tc

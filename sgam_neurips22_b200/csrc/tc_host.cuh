@@ -57,4 +57,8 @@ struct TcParams;
 bool tc2_applicable(int B, int Ho, int Wo, int N, int stride, int out_nchw, int n_valid, int *BN_out);
 int launch_tc2(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, TcParams p,
                int B, int Ho, int Wo, int N, cudaStream_t s);
+// swapped-operand kernel for 128-channel convolutions (net_tc3.cu)
+bool swap_applicable(int B, int Ho, int Wo, int Cin, int Cout, int stride, bool fp32_nhwc_only);
+int launch_conv_swap(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, TcParams p, int B, int H, int W, int Cin,
+                     int Cout, int ksize, cudaStream_t s);
 }  // namespace tc
