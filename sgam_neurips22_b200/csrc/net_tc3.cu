@@ -228,10 +228,12 @@ namespace tc {
 // Does the swapped-operand kernel apply?  128 output channels, stride 1, plain fp32 NHWC output, an image that tiles
 // exactly into 256-pixel boxes whose rows are a multiple of 32 pixels, and enough boxes to fill the machine.
 bool swap_applicable(int B, int Ho, int Wo, int Cin, int Cout, int stride, bool fp32_nhwc_only) {
-    if (!swap_mode() || Cout != 128 || stride != 1 || !fp32_nhwc_only || Cin % 64) return false;
+    static int max_c = -1;                       // SGAM_TC_SWAP_MAXC: largest channel count routed here (experiment knob)
+    if (max_c < 0) { const char *e = getenv("SGAM_TC_SWAP_MAXC"); max_c = e ? atoi(e) : 128; }
+    if (!swap_mode() || Cout % 128 || Cout > max_c || stride != 1 || !fp32_nhwc_only || Cin % 64) return false;
     const bool exact = (Wo >= 256) ? (Wo % 256 == 0) : (Wo >= 32 && (Wo & (Wo - 1)) == 0 && Ho % (256 / Wo) == 0);
     if (!exact) return false;
-    return (long long)B * Ho * Wo / 256 >= sm_count_cached();
+    return (long long)B * Ho * Wo / 256 * (Cout / 128) >= sm_count_cached();
 }
 
 int launch_conv_swap(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, TcParams p, int B, int H, int W, int Cin,
