@@ -14,6 +14,14 @@ x, _, mask, _ = model.get_x(b, ds, return_extrapolation_mask=True, no_depth_rang
 decs, _, pre, quants = model(x, topk=1, extrapolation_mask=mask, get_pre_quantized_feature=True, get_quantized_feature=True)
 rgb, depth = ops.frame_outputs(decs[0][0], ds)
 torch.cuda.synchronize()
+# swapped-operand GEMM (needs a full grid: 256 pixel boxes) with residual + fused GroupNorm statistics
+g = torch.Generator().manual_seed(1)
+xa = torch.randn(1, 256, 256, 128, generator=g).cuda()
+wa = (torch.randn(128, 9 * 128, generator=g) * 0.03).cuda()
+ya = ops.conv2d_tc(ops.split_bf16(xa), ops.split_weight(wa, pad_rows_to=32), torch.zeros(128, device="cuda"), residual=xa, ksize=3, gn_stats=True)
+hi_a, lo_a = ops.groupnorm_split(ya, torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"), True)
+torch.cuda.synchronize()
+print("swap ok", float(ya.double().sum()), float(hi_a.float().abs().mean()))
 # RGB-D integration kernels on a small volume
 from sgam_neurips22_b200.tsdf import TSDFVolume, frustum_box
 K = np.array([[124.4, 0, 32.0], [0, 124.4, 32.0], [0, 0, 1.0]])
@@ -31,8 +39,8 @@ import hashlib
 print("step ok", float(decs[0][0].abs().mean()), hashlib.sha256(decs[0][0].cpu().numpy().tobytes()).hexdigest()[:16])
 PY
 echo "=== plain run (the sanitizer runs must reproduce this checksum) ==="
-python /tmp/san_step.py 2>&1 | grep -E "step ok|tsdf ok"
+python /tmp/san_step.py 2>&1 | grep -E "step ok|tsdf ok|swap ok"
 for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
   echo "=== compute-sanitizer --tool $tool ==="
-  timeout -s KILL 900 compute-sanitizer --tool $tool python /tmp/san_step.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|step ok|tsdf ok|Error|hazard" | head -8
+  timeout -s KILL 900 compute-sanitizer --tool $tool python /tmp/san_step.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|step ok|tsdf ok|swap ok|Error|hazard" | head -8
 done
