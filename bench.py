@@ -443,9 +443,9 @@ def main():
         yy, xx = np.meshgrid(np.linspace(0, 1, 256), np.linspace(0, 1, 256), indexing="ij")
         seeds = [(rng.integers(0, 256, (256, 256, 3)).astype(np.uint8),
                   (lo + (hi - lo) * (0.5 + 0.3 * np.sin(3 * xx + t) * np.cos(2 * yy))).astype(np.float32)) for t in range(B)]
-        dim = (4, 5) if ds == "clevr-infinite" else (20, 1)
+        dim = (6, 6) if ds == "clevr-infinite" else (36, 1)
         tb = TrajectoryBatch(model, ds, seeds, micro_batch=B, output_dim=dim, output_root=tempfile.mkdtemp(prefix="sgam_bench_tb_"))
-        skip = 4
+        skip = 5
         for i in range(tb.n_steps):
             if i == skip:
                 torch.cuda.synchronize()
