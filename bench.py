@@ -8,13 +8,19 @@
 
 One step = one pass of the hot path (forward splat + hole fill + depth code -> VQGAN encode -> codebook arg-min ->
 decode -> uint8 / metric-depth conversion) over `--batch` independent trajectories' frames of synthetic 256x256
-RGB-D (BASELINE.json configs[1], CLEVR-Infinite; `--dataset google_earth` gives the configs[2]-shaped step).
+RGB-D (BASELINE.json configs[1], CLEVR-Infinite).  The other configurations of BASELINE.json ride along as named
+sub-records of the same JSON line (`configs`): configs[2] (GoogleEarth 256x256 scene loop with
+use_rgbd_integration=True), configs[3] (lock-step trajectory batches on every rank + the final map all-gather at its
+real size) and configs[4] (GoogleEarth 512x512, 100-step trajectory per GPU), each with its own `roofline` / `e2e`.
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for what each key means.
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import sys
+import tempfile
 import threading
 import time
 
@@ -89,6 +95,14 @@ def time_steps(fn, steps, world):
     return float(ms.item())
 
 
+def max_over_ranks(seconds, world):
+    import torch.distributed as dist
+    t = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference_fps(state_dict, batch_np, dataset, min_seconds, max_frames):
     """The reference's CPU path (oracle port: same ATen fp32 operators, all host threads) on a bounded sample."""
@@ -126,7 +140,7 @@ def run_reference(args, rank):
         omodel.scene_step(sd, batch_np, args.dataset)
     dt = time.perf_counter() - t0
     fps = args.steps / dt
-    cfg = workload_config(args, 1)
+    cfg = workload_config(args.dataset, args.res, args.batch, 1)
     cfg["frames_per_step"] = 1
     emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -138,12 +152,12 @@ def run_reference(args, rank):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(args, world):
-    name = "CLEVR-Infinite" if args.dataset == "clevr-infinite" else "GoogleEarth-Infinite"
-    return {"workload": f"{name} {args.res}x{args.res} full scene-gen step (forward splat + VQGAN encode + VQ arg-min + decode), "
-                        f"{args.batch} independent trajectories per GPU",
-            "dataset": args.dataset, "resolution": args.res, "trajectories_per_gpu": args.batch,
-            "frames_per_step": args.batch * world, "parallelism": f"dp{world} (trajectory sharding, no collective in the loop)",
+def workload_config(ds, res, batch, world):
+    name = "CLEVR-Infinite" if ds == "clevr-infinite" else "GoogleEarth-Infinite"
+    return {"workload": f"{name} {res}x{res} full scene-gen step (forward splat + VQGAN encode + VQ arg-min + decode), "
+                        f"{batch} independent trajectories per GPU",
+            "dataset": ds, "resolution": res, "trajectories_per_gpu": batch,
+            "frames_per_step": batch * world, "parallelism": f"dp{world} (trajectory sharding, no collective in the loop)",
             "weights": "random init (no checkpoint ships with the reference), N(0,1) codebook",
             "l2": "per-step working set (271 MB fp32 weights + >1 GB activations per frame) exceeds the 126 MB L2; no explicit flush"}
 
@@ -156,6 +170,259 @@ def emit(line):
 
 
 _REAL_STDOUT = 1
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def synthetic_seed_frame(ds, t=0, res=256):
+    from sgam_neurips22_b200 import synthetic
+    rng = np.random.default_rng(1000 + t)
+    lo, hi = synthetic.DATASETS[ds]["depth"]
+    yy, xx = np.meshgrid(np.linspace(0, 1, res), np.linspace(0, 1, res), indexing="ij")
+    return (rng.integers(0, 256, (res, res, 3)).astype(np.uint8),
+            (lo + (hi - lo) * (0.5 + 0.3 * np.sin(3 * xx + t) * np.cos(2 * yy))).astype(np.float32))
+
+
+class StepHarness:
+    """One scene-generation step over B trajectories of one GPU, three ways: device-resident kernels (`resident`), the
+    same replayed as a CUDA graph (`run`), and through the public API from pinned host buffers (`e2e`)."""
+
+    def __init__(self, model, ds, res, B, seed, dev, use_graph=True):
+        from sgam_neurips22_b200 import _lib, ops, synthetic
+        self.model, self.ds, self.res, self.B, self.dev, self.ops = model, ds, res, B, dev, ops
+        self.lib = _lib.load()
+        self.eng = model.engine
+        self.batch_np = synthetic.scene_step_batch(ds, res=res, batch=B, seed=seed)
+        self.N = self.batch_np["src_depths"].shape[1]
+        self.host = {k: torch.from_numpy(v).pin_memory() for k, v in self.batch_np.items()}
+        host = self.host
+        self.r_rgb, self.r_dep = host["src_imgs"].to(dev), host["src_depths"].to(dev)
+        self.Kinv = model._kinv(host["Ks"])
+        self.K_tgt = host["Ks"][:, 0].contiguous().to(dev)
+        T = torch.eye(4).repeat(B, self.N, 1, 1)
+        T[..., :3, :3], T[..., :3, 3] = host["R_rels"], host["t_rels"]
+        self.T = T.to(dev)
+        self.ws = torch.empty(B * res * res, dtype=torch.int64, device=dev)
+        self.out_rgb = torch.empty(B, res, res, 3, dtype=torch.uint8, device=dev)
+        self.out_depth = torch.empty(B, res, res, device=dev)
+        c0 = self.lib.sgam_launch_count()
+        self.resident()
+        torch.cuda.synchronize()
+        self.launches_per_step = int(self.lib.sgam_launch_count() - c0)
+        self.graph = None
+        self.run = self.resident
+        if use_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.resident()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.resident()
+            self.run = self.graph.replay
+        # end-to-end leg: pinned host buffers in, pinned host buffers out
+        self.pin_rgb = torch.empty(B, res, res, 3, dtype=torch.uint8).pin_memory()
+        self.pin_depth = torch.empty(B, res, res).pin_memory()
+        self.api_batch = {k: host[k] for k in ("src_imgs", "src_depths", "Ks", "R_rels", "t_rels", "dst_img", "dst_depth")}
+        self.api_batch["_dst_placeholder"] = True        # what the scene loop passes: all-zero target placeholders
+        self.h2d = sum(host[k].numel() * host[k].element_size() for k in ("src_imgs", "src_depths", "Ks", "R_rels", "t_rels"))
+        self.d2h = self.pin_rgb.numel() + self.pin_depth.numel() * 4
+
+    def splat(self):
+        return self.ops.splat_forward(self.r_rgb, self.r_dep, self.K_tgt, self.Kinv, self.T, self.ds, channels_last=True,
+                                      workspace=self.ws)
+
+    def resident(self):
+        s = self.splat()
+        dec, pre, zq, idx = self.eng.forward(s["x"], s["mask"])
+        self.ops.frame_outputs(dec, self.ds, rgb_u8=self.out_rgb, depth=self.out_depth)
+        return dec
+
+    def e2e(self):
+        b = dict(self.api_batch)
+        x, _, mask, _ = self.model.get_x(b, self.ds, return_extrapolation_mask=True, no_depth_range=True, parallel=True)
+        decs, _, pre, quants = self.model(x, topk=1, extrapolation_mask=mask, get_pre_quantized_feature=True,
+                                          get_quantized_feature=True, sample_number=1)
+        rgb, depth = self.ops.frame_outputs(decs[0][0], self.ds, rgb_u8=self.out_rgb, depth=self.out_depth)
+        self.pin_rgb.copy_(rgb, non_blocking=True)
+        self.pin_depth.copy_(depth, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                      # the caller reads the frame before the next step
+
+    def digest(self):
+        """SHA-256 of the step's outputs (uint8 RGB + fp32 depth bytes) after one resident run."""
+        self.run()
+        torch.cuda.synchronize()
+        h = hashlib.sha256()
+        h.update(self.out_rgb.cpu().numpy().tobytes())
+        h.update(self.out_depth.cpu().numpy().tobytes())
+        return h.digest()
+
+    # -- roofline of the dominant kernel family (tcgen05 implicit GEMM + fused attention), CUDA events per call ------
+    def roofline(self, peaks, step_ms, dump=None):
+        ops, eng = self.ops, self.eng
+        events = []
+        stem_w = eng.wsplit.get("encoder.conv_in.padded")
+        cin = eng.dd["in_channels"]
+
+        def first(y):
+            while isinstance(y, (tuple, list)):
+                y = y[0]
+            return y
+
+        def tensor_bytes(a, kw, y):                # algorithmic HBM bytes of one launch: every operand / result tensor once
+            seen, total, stack = set(), 0, [list(a), y, kw.get("residual"), kw.get("bias_m")]
+            while stack:
+                t = stack.pop()
+                if isinstance(t, (tuple, list)):
+                    stack.extend(t)
+                elif torch.is_tensor(t) and t.data_ptr() not in seen:
+                    seen.add(t.data_ptr())
+                    total += t.numel() * t.element_size()
+            return total
+
+        def conv_flops(a, kw, y):                  # 2 * output elements (Cout incl.) * K
+            w = a[1][0] if isinstance(a[1], tuple) else a[1]
+            cout = kw.get("cout") or w.shape[0]
+            K = w.shape[1]
+            if stem_w is not None and a[1] is stem_w:
+                K = 9 * cin                        # the zero-padded stem: count its REAL 9*4 taps, not the 9*64 issued
+            return 2.0 * (first(y).numel() // cout) * cout * K
+
+        def gemm_flops(a, kw, y):
+            return 2.0 * first(y).numel() * a[0][0].shape[-1]
+
+        def attn_flops(a, kw, y):                  # QK^T + PV
+            q = a[0][0]
+            Bq, T, C = q.shape
+            return 4.0 * Bq * T * T * C
+
+        def timed(fn, flops_of):
+            def wrapper(*a, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                y = fn(*a, **kw)
+                e1.record()
+                shp = tuple(a[0][0].shape) + tuple((a[1][0] if isinstance(a[1], tuple) else a[1]).shape)
+                events.append((e0, e1, flops_of(a, kw, y), fn.__name__, shp,
+                               {k: v for k, v in kw.items() if isinstance(v, (int, float, bool))}, tensor_bytes(a, kw, y)))
+                return y
+            return wrapper
+
+        patched = {"conv2d_tc": (ops.conv2d_tc, conv_flops), "gemm_nt_tc": (ops.gemm_nt_tc, gemm_flops)}
+        if hasattr(ops, "attention_tc"):
+            patched["attention_tc"] = (ops.attention_tc, attn_flops)
+        for name, (fn, fl) in patched.items():
+            setattr(ops, name, timed(fn, fl))
+        try:
+            for _ in range(2):
+                events.clear()
+                self.resident()
+                torch.cuda.synchronize()
+        finally:
+            for name, (fn, fl) in patched.items():
+                setattr(ops, name, fn)
+        ms = sum(ev[0].elapsed_time(ev[1]) for ev in events)
+        flops = sum(ev[2] for ev in events)
+        if dump:
+            with open(dump, "w") as f:
+                f.write("op\tshape(A|B)\tkw\tGFLOP\tms\tTFLOP/s(algorithmic)\n")
+                for ev in events:
+                    t = ev[0].elapsed_time(ev[1])
+                    f.write(f"{ev[3]}\t{ev[4]}\t{ev[5]}\t{ev[2] / 1e9:.2f}\t{t:.4f}\t{ev[2] / t / 1e9:.1f}\n")
+        tflops = flops / (ms * 1e-3) / 1e12
+        nsplit = eng.nsplit if eng.mode == "tc" else 1
+        by_op = {}
+        for ev in events:
+            d = by_op.setdefault(ev[3], [0, 0.0, 0.0])
+            d[0] += 1; d[1] += ev[0].elapsed_time(ev[1]); d[2] += ev[2]
+        return {"kernel": "tcgen05 implicit-GEMM convolutions (tc_gemm / tc_gemm2 / tc_gemm_swap) + fused attention (attn_fwd)",
+                "bound": "tensor", "achieved": tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tflops / peaks["tflops"],
+                "algorithmic_bytes_per_launch": sum(ev[6] for ev in events) / max(1, len(events)),
+                "peak_source": peaks["source"] + ", sustained bf16",
+                "launches_per_step": len(events), "ms_per_step": ms, "share_of_step": ms / step_ms,
+                "flops_per_step": flops, "mma_issue_tflops": tflops * nsplit, "frac_mma_issue": tflops * nsplit / peaks["tflops"],
+                "by_op": {k: {"calls": v[0], "ms": v[1], "tflops": v[2] / (v[1] * 1e-3) / 1e12} for k, v in by_op.items()},
+                "note": "achieved counts ALGORITHMIC flops (2*M*N*K of the fp32 conv / attention products, the zero-padded "
+                        "stem at its real K); every product is issued as 3 bf16 MMAs (hi*hi + hi*lo + lo*hi) to stay within "
+                        "1e-3 of the fp32 reference, so the tensor pipe runs at mma_issue_tflops"}
+
+
+def measure(h, steps, warmup, world):
+    """-> (value leg ms, e2e leg ms, e2e steps)."""
+    for _ in range(warmup):
+        h.run()
+    ms = time_steps(h.run, steps, world)
+    for _ in range(warmup):
+        h.e2e()
+    e2e_steps = max(3, min(steps, 20))
+    ms_e2e = time_steps(h.e2e, e2e_steps, world)
+    return ms, ms_e2e, e2e_steps
+
+
+def latest_traffic():
+    """DRAM bytes per GEMM launch from the newest committed ncu launch list (profiles/r*_traffic.json)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    tj = json.load(open(files[-1]))
+    return tj["dram_bytes_per_launch"], tj["source"]
+
+
+def scene_loop(model, ds, res, dim, rgbd, world, all_ranks, read_back=False, skip=5):
+    """Sequential frames of ONE trajectory per participating rank through InfiniteSceneGeneration.one_step_prediction
+    (source selection, pose math, splat or TSDF + inverse warp, forward, uint8 / depth conversion; no disk).  Wall clock
+    between device synchronisations, max over the participating ranks.  read_back: every generated frame is also copied
+    to pinned host memory and the host waits for it (the end-to-end variant)."""
+    from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration
+    rank = int(os.environ.get("RANK", 0))
+    pipe = InfiniteSceneGeneration(model, ds, seed_frame=synthetic_seed_frame(ds, rank, 256), output_dim=dim,
+                                   use_rgbd_integration=rgbd, image_resolution=(res, res),
+                                   output_root=tempfile.mkdtemp(prefix="sgam_bench_loop_"))
+    pin_rgb = torch.empty(res, res, 3, dtype=torch.uint8).pin_memory()
+    pin_depth = torch.empty(res, res).pin_memory()
+    n_loop = dim[0] * dim[1] - 1
+    from sgam_neurips22_b200 import ops as _ops
+    real_h2d, counted = _ops.h2d, [0]
+
+    def counting_h2d(t, device, dtype=None):                  # every host->device upload of the loop goes through ops.h2d
+        out = real_h2d(t, device, dtype)
+        counted[0] += out.numel() * out.element_size()
+        return out
+    _ops.h2d = counting_h2d
+    try:
+        return _scene_loop_body(pipe, n_loop, skip, all_ranks, world, read_back, pin_rgb, pin_depth, counted)
+    finally:
+        _ops.h2d = real_h2d
+
+
+def _scene_loop_body(pipe, n_loop, skip, all_ranks, world, read_back, pin_rgb, pin_depth, counted):
+    for i in range(n_loop):
+        if i == skip:
+            if all_ranks and world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize()
+            t0, b0 = time.perf_counter(), counted[0]
+        coord = pipe.next_pose(pipe.curr)
+        pipe.one_step_prediction(coord, save_res_to_disk=False)
+        if read_back:
+            rgb, depth = pipe._frames[tuple(coord)]
+            pin_depth.copy_(depth, non_blocking=True)
+            pin_rgb.copy_(torch.round((rgb + 1.0) * 127.5).to(torch.uint8), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        pipe.curr += 1
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if all_ranks:
+        dt = max_over_ranks(dt, world)
+    n = n_loop - skip
+    vol = getattr(pipe, "volume", None)
+    extra = {"h2d_bytes_per_frame": (counted[0] - b0) // max(1, n)}
+    if vol is not None and hasattr(vol, "memory_bytes"):
+        extra["tsdf_volume_bytes"] = int(vol.memory_bytes())
+    return n, dt, extra
 
 
 def main():
@@ -173,8 +440,11 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="independent trajectories per GPU (BASELINE.json configs[3]: 64 over 8 GPUs)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2..4] sub-records (headline only)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
+    ap.add_argument("--profile-loop", action="store_true",
+                    help="with --profile-step: profile 3 frames of the configs[2] scene loop (TSDF + inverse warp) instead")
     ap.add_argument("--dump-gemm", default=None, help="write the per-launch table of the tensor-core GEMMs of one step to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -194,299 +464,256 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    from sgam_neurips22_b200 import _lib, ops, synthetic
+    from sgam_neurips22_b200 import ops, synthetic
     from sgam_neurips22_b200 import dist as sdist
     from sgam_neurips22_b200.model import VQModel
-    lib = _lib.load()
     peaks = load_peaks()
     ds, B, res = args.dataset, args.batch, args.res
+    models = {}
 
-    model = synthetic.randomize_weights(VQModel(**synthetic.model_kwargs(ds)), seed=0).to(dev).eval()
+    def get_model(name):
+        if name not in models:
+            models[name] = synthetic.randomize_weights(VQModel(**synthetic.model_kwargs(name)), seed=0).to(dev).eval()
+        return models[name]
+
+    model = get_model(ds)
     eng = model.engine
-    batch_np = synthetic.scene_step_batch(ds, res=res, batch=B, seed=100 + rank)
-    N = batch_np["src_depths"].shape[1]
 
-    # ---------------- device-resident leg (`value`) -----------------------------------------------------------
-    host = {k: torch.from_numpy(v).pin_memory() for k, v in batch_np.items()}
-    r_rgb, r_dep = host["src_imgs"].to(dev), host["src_depths"].to(dev)
-    Kinv = model._kinv(host["Ks"])
-    K_tgt = host["Ks"][:, 0].contiguous().to(dev)
-    T = torch.eye(4).repeat(B, N, 1, 1)
-    T[..., :3, :3], T[..., :3, 3] = host["R_rels"], host["t_rels"]
-    T = T.to(dev)
-    ws = torch.empty(B * res * res, dtype=torch.int64, device=dev)
-    out_rgb = torch.empty(B, res, res, 3, dtype=torch.uint8, device=dev)
-    out_depth = torch.empty(B, res, res, device=dev)
-
-    def step_resident():
-        s = ops.splat_forward(r_rgb, r_dep, K_tgt, Kinv, T, ds, channels_last=True, workspace=ws)
-        dec, pre, zq, idx = eng.forward(s["x"], s["mask"])
-        ops.frame_outputs(dec, ds, rgb_u8=out_rgb, depth=out_depth)
-        return dec
-
-    c0 = lib.sgam_launch_count()
-    step_resident()
-    torch.cuda.synchronize()
-    launches_per_step = int(lib.sgam_launch_count() - c0)
-
-    if args.profile_step:
-        for _ in range(2):
-            step_resident()
-        torch.cuda.synchronize()
-        torch.cuda.cudart().cudaProfilerStart()
-        step_resident()
+    if args.profile_step and args.profile_loop:
+        from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration
+        gm = get_model("google_earth")
+        pipe = InfiniteSceneGeneration(gm, "google_earth", seed_frame=synthetic_seed_frame("google_earth"), output_dim=(12, 1),
+                                       use_rgbd_integration=True, output_root=tempfile.mkdtemp(prefix="sgam_prof_"))
+        for i in range(11):
+            if i == 8:
+                torch.cuda.synchronize()
+                torch.cuda.cudart().cudaProfilerStart()
+            pipe.one_step_prediction(pipe.next_pose(pipe.curr), save_res_to_disk=False)
+            pipe.curr += 1
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         return
 
-    run_step = step_resident
-    graph = None
-    if not args.no_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            step_resident()
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step_resident()
-        run_step = graph.replay
+    h = StepHarness(model, ds, res, B, 100 + rank, dev, use_graph=not args.no_graph)
+    if args.profile_step:
+        for _ in range(2):
+            h.resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        h.resident()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
 
+    # ---------------- headline: device-resident leg (`value`) and end-to-end leg (`e2e`) ---------------------------------
     for _ in range(args.warmup):
-        run_step()
+        h.run()
     sampler = ClockSampler(local)
     sampler.start()
-    ms = time_steps(run_step, args.steps, world)
+    ms = time_steps(h.run, args.steps, world)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    frames = B * world * args.steps
-    value = frames / (ms / 1000.0)
-
-    # ---------------- end-to-end leg (`e2e`): public API, host buffers, H2D + D2H inside the timed region --------
-    pin_rgb = torch.empty(B, res, res, 3, dtype=torch.uint8).pin_memory()
-    pin_depth = torch.empty(B, res, res).pin_memory()
-    api_batch = {k: host[k] for k in ("src_imgs", "src_depths", "Ks", "R_rels", "t_rels", "dst_img", "dst_depth")}
-    h2d = sum(api_batch[k].numel() * api_batch[k].element_size() for k in ("src_imgs", "src_depths", "Ks", "R_rels", "t_rels"))
-    d2h = pin_rgb.numel() + pin_depth.numel() * 4
-
-    def step_e2e():
-        b = dict(api_batch)
-        x, _, mask, _ = model.get_x(b, ds, return_extrapolation_mask=True, no_depth_range=True, parallel=True)
-        decs, _, pre, quants = model(x, topk=1, extrapolation_mask=mask, get_pre_quantized_feature=True,
-                                     get_quantized_feature=True, sample_number=1)
-        rgb, depth = ops.frame_outputs(decs[0][0], ds, rgb_u8=out_rgb, depth=out_depth)
-        pin_rgb.copy_(rgb, non_blocking=True)
-        pin_depth.copy_(depth, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                      # the caller reads the frame before the next step
-
+    value = B * world * args.steps / (ms / 1000.0)
     for _ in range(args.warmup):
-        step_e2e()
+        h.e2e()
     e2e_steps = max(3, min(args.steps, 20))
-    ms_e2e = time_steps(step_e2e, e2e_steps, world)
+    ms_e2e = time_steps(h.e2e, e2e_steps, world)
     e2e_value = B * world * e2e_steps / (ms_e2e / 1000.0)
+    roof = h.roofline(peaks, ms / args.steps, dump=args.dump_gemm if rank == 0 else None)
+    traffic, traffic_src = latest_traffic() if (ds == "clevr-infinite" and B == 8 and res == 256) else (None, None)
+    roof["traffic"], roof["traffic_source"] = traffic, traffic_src
 
-    # ---------------- roofline of the dominant kernel (tcgen05 implicit GEMM), measured live with CUDA events ------------
-    gemm_events = []
-
-    def timed(fn, flops_of):
-        def wrapper(*a, **kw):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            y = fn(*a, **kw)
-            e1.record()
-            shp = tuple(a[0][0].shape) + tuple((a[1][0] if isinstance(a[1], tuple) else a[1]).shape)
-            gemm_events.append((e0, e1, flops_of(a, kw, y), fn.__name__, shp, {k: v for k, v in kw.items() if isinstance(v, (int, float, bool))},
-                                tensor_bytes(a, kw, y)))
-            return y
-        return wrapper
-
-    def first(y):
-        while isinstance(y, (tuple, list)):
-            y = y[0]
-        return y
-
-    def tensor_bytes(a, kw, y):                    # algorithmic HBM bytes of one launch: every operand / result tensor once
-        seen, total, stack = set(), 0, [a[0], a[1], y, kw.get("residual"), kw.get("bias_m")]
-        while stack:
-            t = stack.pop()
-            if isinstance(t, (tuple, list)):
-                stack.extend(t)
-            elif torch.is_tensor(t) and t.data_ptr() not in seen:
-                seen.add(t.data_ptr())
-                total += t.numel() * t.element_size()
-        return total
-
-    def conv_flops(a, kw, y):                      # 2 * output elements (Cout incl.) * K
-        w = a[1][0] if isinstance(a[1], tuple) else a[1]
-        cout = kw.get("cout") or w.shape[0]
-        return 2.0 * (first(y).numel() // cout) * cout * w.shape[1]
-
-    def gemm_flops(a, kw, y):
-        return 2.0 * first(y).numel() * a[0][0].shape[-1]
-
-    patched = {"conv2d_tc": (ops.conv2d_tc, conv_flops), "gemm_nt_tc": (ops.gemm_nt_tc, gemm_flops)}
-    for name, (fn, fl) in patched.items():
-        setattr(ops, name, timed(fn, fl))
-    try:
-        for _ in range(2):
-            gemm_events.clear()
-            step_resident()
-            torch.cuda.synchronize()
-    finally:
-        for name, (fn, fl) in patched.items():
-            setattr(ops, name, fn)
-    conv_ms = sum(ev[0].elapsed_time(ev[1]) for ev in gemm_events)
-    conv_flops_total = sum(ev[2] for ev in gemm_events)
-    if args.dump_gemm and rank == 0:
-        with open(args.dump_gemm, "w") as f:
-            f.write("op\tshape(A|B)\tkw\tGFLOP\tms\tTFLOP/s(algorithmic)\n")
-            for ev in gemm_events:
-                t = ev[0].elapsed_time(ev[1])
-                f.write(f"{ev[3]}\t{ev[4]}\t{ev[5]}\t{ev[2] / 1e9:.2f}\t{t:.4f}\t{ev[2] / t / 1e9:.1f}\n")
-    conv_tflops = conv_flops_total / (conv_ms * 1e-3) / 1e12
-    gemm_alg_bytes = sum(ev[6] for ev in gemm_events) / max(1, len(gemm_events))
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath) and ds == "clevr-infinite" and B == 8 and res == 256:      # the configuration the capture was taken on
-        tj = json.load(open(tpath))
-        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-    nsplit = eng.nsplit if eng.mode == "tc" else 1
+    # ---------------- 1-rank identity: every rank's frames are what ONE GPU computes for the same inputs ------------------
+    rank_identity = None
+    if world > 1:
+        mine = torch.tensor(list(h.digest()), dtype=torch.uint8, device=dev)
+        allg = torch.empty(world * 32, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allg, mine)
+        if rank == 0:
+            allg = allg.cpu().numpy().reshape(world, 32)
+            for r in range(1, world):
+                hr = StepHarness(model, ds, res, B, 100 + r, dev, use_graph=False)
+                got = np.frombuffer(hr.digest(), np.uint8)
+                if not np.array_equal(got, allg[r]):
+                    raise SystemExit(f"bench.py: rank {r}'s frames differ from a 1-rank run of the same trajectories")
+                del hr
+            rank_identity = {"ranks_checked": world, "bit_identical_to_1_rank": True,
+                             "how": "SHA-256 of every rank's uint8 RGB + fp32 depth for its step inputs, all-gathered; rank 0 "
+                                    "recomputed every other rank's trajectories on its own GPU and compared the digests"}
+            log(f"rank identity: the frames of all {world} ranks are bit-identical to 1-rank runs of the same trajectories")
 
     def solo(fn, n=20):
         for _ in range(3):
             fn()
         return time_steps(fn, n, 1) / n
 
-    splat_ms = solo(lambda: ops.splat_forward(r_rgb, r_dep, K_tgt, Kinv, T, ds, channels_last=True, workspace=ws))
+    N = h.N
+    splat_ms = solo(h.splat)
     splat_bytes = B * (N * res * res * 16 + res * res * 17)
-    pre = eng.encode(step_in_x := ops.splat_forward(r_rgb, r_dep, K_tgt, Kinv, T, ds, channels_last=True, workspace=ws)["x"], None)
+    pre = eng.encode(h.splat()["x"], None)
     vq_ms = solo(lambda: eng.quantize(pre))
     vq_simt_ms = solo(lambda: ops.vq_nearest(pre.view(-1, pre.shape[-1]), eng.p["quantize.embedding.weight"]))
     Tk, D = pre.numel() // pre.shape[-1], pre.shape[-1]
     vq_bytes = eng.n_embed * D * 4 + 2 * Tk * D * 4 + Tk * 8
     vq_flops = 2.0 * Tk * eng.n_embed * D
-    del step_in_x
 
     # ---------------- single-trajectory latency (batch 1: the reference's own operating point) ---------------------------
     single = None
     if B != 1:
-        b1 = {k: v[:1].contiguous() for k, v in host.items()}
-        s_rgb, s_dep = b1["src_imgs"].to(dev), b1["src_depths"].to(dev)
-        s_Kinv, s_Kt, s_T = Kinv[:1].contiguous(), K_tgt[:1].contiguous(), T[:1].contiguous()
-        s_ws = torch.empty(res * res, dtype=torch.int64, device=dev)
-        s_out_rgb = torch.empty(1, res, res, 3, dtype=torch.uint8, device=dev)
-        s_out_depth = torch.empty(1, res, res, device=dev)
-
-        def step_single():
-            s = ops.splat_forward(s_rgb, s_dep, s_Kt, s_Kinv, s_T, ds, channels_last=True, workspace=s_ws)
-            dec, _, _, _ = eng.forward(s["x"], s["mask"])
-            ops.frame_outputs(dec, ds, rgb_u8=s_out_rgb, depth=s_out_depth)
-
-        run_single = step_single
-        step_single()
-        if not args.no_graph:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step_single()
-            torch.cuda.current_stream().wait_stream(side)
-            g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                step_single()
-            run_single = g1.replay
+        h1 = StepHarness(model, ds, res, 1, 100 + rank, dev, use_graph=not args.no_graph)
         for _ in range(args.warmup):
-            run_single()
-        ms1 = time_steps(run_single, args.steps, world)
+            h1.run()
+        ms1 = time_steps(h1.run, args.steps, world)
         single = {"value": world * args.steps / (ms1 / 1000.0), "unit": UNIT, "ms_per_frame": ms1 / args.steps,
+                  "gpu_launches_per_frame": h1.launches_per_step,
                   "note": "one trajectory per GPU (batch 1), inputs resident, CUDA graph"}
+        del h1
 
     # ---------------- the drop-in scene loop itself (sequential frames of ONE trajectory through InfiniteSceneGeneration) ----
-    scene_loop = None
+    loop_rec = None
     if rank == 0:
-        import tempfile
-        from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration
-        cwd = os.getcwd()
-        os.chdir(tempfile.mkdtemp(prefix="sgam_bench_"))
-        try:
-            rng = np.random.default_rng(0)
-            lo, hi = synthetic.DATASETS[ds]["depth"]
-            yy, xx = np.meshgrid(np.linspace(0, 1, 256), np.linspace(0, 1, 256), indexing="ij")
-            seed = (rng.integers(0, 256, (256, 256, 3)).astype(np.uint8),
-                    (lo + (hi - lo) * (0.5 + 0.3 * np.sin(3 * xx) * np.cos(2 * yy))).astype(np.float32))
-            dim = (5, 6) if ds == "clevr-infinite" else (30, 1)
-            rgbd = ds == "google_earth"          # BASELINE.json configs[2]: the GoogleEarth loop runs with use_rgbd_integration=True
-            pipe = InfiniteSceneGeneration(model, ds, seed_frame=seed, output_dim=dim, use_rgbd_integration=rgbd)
-            n_loop, skip = dim[0] * dim[1] - 1, 5
-            for i in range(n_loop):
-                if i == skip:
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                pipe.one_step_prediction(pipe.next_pose(pipe.curr), save_res_to_disk=False)
-                pipe.curr += 1
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            scene_loop = {"value": (n_loop - skip) / dt, "unit": UNIT, "ms_per_frame": 1000.0 * dt / (n_loop - skip), "frames": n_loop - skip,
-                          "note": "InfiniteSceneGeneration.one_step_prediction, one trajectory, frames generated sequentially from the "
-                                  "device-resident frame store (source selection, pose math, splat, forward, uint8/depth conversion), "
-                                  "no disk writes, wall clock on rank 0" +
-                                  ("; use_rgbd_integration=True: device TSDF integration + ray-cast target depth + inverse warp" if rgbd else "")}
-        finally:
-            os.chdir(cwd)
+        dim = (5, 6) if ds == "clevr-infinite" else (30, 1)
+        n, dt, _ = scene_loop(model, ds, res, dim, False, world, all_ranks=False)
+        loop_rec = {"value": n / dt, "unit": UNIT, "ms_per_frame": 1000.0 * dt / n, "frames": n,
+                    "note": "InfiniteSceneGeneration.one_step_prediction, one trajectory, frames generated sequentially from the "
+                            "device-resident frame store (source selection, pose math, splat, forward, uint8/depth conversion), "
+                            "no disk writes, wall clock on rank 0"}
 
-    # ---------------- B trajectories in lock-step through the real scene loop (TrajectoryBatch = the configs[3] API) -----
+    configs = {}
+    if not args.no_configs:
+        # ---------------- configs[2]: GoogleEarth 256x256 scene loop with use_rgbd_integration=True, 1 x B200 (rank 0) --------
+        if rank == 0:
+            gm = get_model("google_earth")
+            n, dt, extra = scene_loop(gm, "google_earth", 256, (60, 1), True, world, all_ranks=False)
+            n2, dt2, extra2 = scene_loop(gm, "google_earth", 256, (40, 1), True, world, all_ranks=False, read_back=True)
+            h2 = StepHarness(gm, "google_earth", 256, 1, 100, dev, use_graph=not args.no_graph)
+            for _ in range(args.warmup):
+                h2.run()
+            ms2 = time_steps(h2.run, args.steps, 1) / args.steps
+            roof2 = h2.roofline(peaks, ms2)
+            configs["configs[2]"] = {
+                "workload": "GoogleEarth-Infinite 256x256 scene-gen loop with use_rgbd_integration=True, one trajectory on one GPU: "
+                            "device TSDF integration of the selected sources + ray-cast target depth + inverse warp + forward",
+                "value": n / dt, "unit": UNIT, "ms_per_frame": 1000.0 * dt / n, "frames": n, **extra,
+                "e2e": {"value": n2 / dt2, "unit": UNIT, "h2d_bytes_per_step": int(extra2["h2d_bytes_per_frame"]),
+                        "d2h_bytes_per_step": 256 * 256 * 7, "frames": n2,
+                        "api": "InfiniteSceneGeneration.one_step_prediction(save_res_to_disk=False) + read-back of the frame to "
+                               "pinned host memory every step; the frame store itself is device-resident by design"},
+                "network_step_ms": ms2, "roofline": roof2}
+            del h2
+        # ---------------- configs[4]: GoogleEarth 512x512, 100-step trajectory, one per GPU on every rank ------------------------
+        gm = get_model("google_earth")
+        n4, dt4, _ = scene_loop(gm, "google_earth", 512, (106, 1), False, world, all_ranks=True)
+        h4 = StepHarness(gm, "google_earth", 512, 1, 100 + rank, dev, use_graph=not args.no_graph)
+        ms4, ms4_e2e, st4 = measure(h4, max(5, min(args.steps, 10)), args.warmup, world)
+        st4v = max(5, min(args.steps, 10))
+        roof4 = h4.roofline(peaks, ms4 / st4v)
+        if rank == 0:
+            configs["configs[4]"] = {
+                "workload": "GoogleEarth-Infinite 512x512, 100-step long-horizon trajectory through InfiniteSceneGeneration, one "
+                            f"trajectory per GPU on {world} GPU(s) (latent 32x32 = 1024 tokens, attention over 16384 tokens)",
+                "value": world * n4 / dt4, "unit": "frames/s @512x512", "ms_per_frame": 1000.0 * dt4 / n4, "frames_per_gpu": n4,
+                "resident_step": {"value": world * st4v / (ms4 / 1000.0), "unit": "frames/s @512x512", "ms_per_step": ms4 / st4v},
+                "e2e": {"value": world * st4 / (ms4_e2e / 1000.0), "unit": "frames/s @512x512", "h2d_bytes_per_step": int(h4.h2d),
+                        "d2h_bytes_per_step": int(h4.d2h), "ms_per_step": ms4_e2e / st4,
+                        "api": "VQModel.get_x + VQModel.forward(topk=1) + frame_outputs, pinned host buffers"},
+                "gpu_launches_per_step": h4.launches_per_step, "roofline": roof4}
+        del h4
+
+    # ---------------- configs[3]: B trajectories per GPU in lock-step through the real scene loop, on EVERY rank ---------------
     traj_batch = None
-    if rank == 0 and B > 1:
-        import tempfile
+    if B > 1:
         from sgam_neurips22_b200.scene_batch import TrajectoryBatch
-        rng = np.random.default_rng(1)
-        lo, hi = synthetic.DATASETS[ds]["depth"]
-        yy, xx = np.meshgrid(np.linspace(0, 1, 256), np.linspace(0, 1, 256), indexing="ij")
-        seeds = [(rng.integers(0, 256, (256, 256, 3)).astype(np.uint8),
-                  (lo + (hi - lo) * (0.5 + 0.3 * np.sin(3 * xx + t) * np.cos(2 * yy))).astype(np.float32)) for t in range(B)]
+        seeds = [synthetic_seed_frame(ds, t) for t in range(B * world)]
         dim = (6, 6) if ds == "clevr-infinite" else (36, 1)
-        tb = TrajectoryBatch(model, ds, seeds, micro_batch=B, output_dim=dim, output_root=tempfile.mkdtemp(prefix="sgam_bench_tb_"))
+        tb = TrajectoryBatch(model, ds, seeds, micro_batch=B, rank=rank, world_size=world, output_dim=dim,
+                             output_root=tempfile.mkdtemp(prefix="sgam_bench_tb_"))
         skip = 5
         for i in range(tb.n_steps):
             if i == skip:
+                if world > 1:
+                    dist.barrier()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
             tb.step()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        traj_batch = {"value": B * (tb.n_steps - skip) / dt, "unit": UNIT, "ms_per_step": 1000.0 * dt / (tb.n_steps - skip),
-                      "trajectories": B, "steps": tb.n_steps - skip,
-                      "note": "TrajectoryBatch.step: the per-GPU trajectories advance in lock-step through InfiniteSceneGeneration's own "
-                              "source selection / batch preparation and ONE batched get_x + forward per step; per-GPU wall clock on rank 0"}
-        del tb
+        dt = max_over_ranks(time.perf_counter() - t0, world)
+        t_g0 = time.perf_counter()
+        xyz, col, (g_rgb, g_depth, g_poses) = tb.gather_map()
+        torch.cuda.synchronize()
+        t_gather = time.perf_counter() - t_g0
+        frames_total = g_rgb.shape[0]
+        ident = None
+        if world > 1 and rank == 0:
+            # trajectories of the LAST rank, re-run on rank 0's GPU, must reproduce that rank's slice of the gathered map
+            r = world - 1
+            solo_tb = TrajectoryBatch(model, ds, seeds, micro_batch=B, rank=r, world_size=world, output_dim=dim,
+                                      output_root=tempfile.mkdtemp(prefix="sgam_bench_tb_solo_"))
+            solo_tb.scene_expansion()
+            s_rgb, s_depth, _ = solo_tb.local_records()
+            F = s_rgb.shape[0]
+            if not (torch.equal(s_rgb, g_rgb[r * F:(r + 1) * F]) and torch.equal(s_depth, g_depth[r * F:(r + 1) * F])):
+                raise SystemExit(f"bench.py: rank {r}'s trajectories differ from a 1-rank re-run (TrajectoryBatch)")
+            ident = True
+            log(f"trajectory batch: rank {r}'s {F} gathered frames are bit-identical to a 1-rank re-run")
+            del solo_tb
+        if rank == 0:
+            traj_batch = {"workload": f"CLEVR-Infinite 256x256, {B * world} independent trajectories sharded over {world} GPU(s), "
+                                      "lock-step scene loop + final map all-gather" if ds == "clevr-infinite" else
+                                      f"{ds} {B * world} trajectories over {world} GPU(s)",
+                          "value": B * world * (tb.n_steps - skip) / dt, "unit": UNIT, "ms_per_step": 1000.0 * dt / (tb.n_steps - skip),
+                          "trajectories": B * world, "steps": tb.n_steps - skip,
+                          "map_frames_gathered": int(frames_total), "map_points": int(xyz.shape[0]), "gather_map_s": t_gather,
+                          "bit_identical_to_1_rank": ident,
+                          "note": "TrajectoryBatch.step on every rank: the per-GPU trajectories advance in lock-step through "
+                                  "InfiniteSceneGeneration's own source selection / batch preparation and ONE batched get_x + forward "
+                                  "per step; wall clock between synchronisations, max over ranks"}
+        del tb, xyz, col, g_rgb, g_depth, g_poses
+        torch.cuda.empty_cache()
 
-    # ---------------- final map all-gather (the only collective; outside the frames/sec region) ----------------------
-    poses = torch.zeros(B, 12, dtype=torch.float64)
-    ag_ms = None
+    # ---------------- final map all-gather at configs[3]'s REAL size (the only collective; outside the frames/sec region) -----
+    allgather = None
     if world > 1:
-        sdist.gather_scene_map(out_rgb, out_depth, poses)
-        ag_ms = time_steps(lambda: sdist.gather_scene_map(out_rgb, out_depth, poses), 5, world) / 5
+        F = 8 * 399                                   # 64 trajectories x 399 generated frames over 8 GPUs -> 3192 frames per rank
+        rec = sdist.record_bytes(256, 256)
+        local_buf = torch.full((F, rec), rank + 1, dtype=torch.uint8, device=dev)
+        out_buf = torch.empty((world * F, rec), dtype=torch.uint8, device=dev)
+        fn = lambda: dist.all_gather_into_tensor(out_buf, local_buf)
+        fn()
+        ag_ms = time_steps(fn, 5, world) / 5
+        ok = all(int(out_buf[r * F, 0]) == r + 1 and int(out_buf[(r + 1) * F - 1, rec - 1]) == r + 1 for r in range(world))
+        del out_buf
+        rgb = local_buf[:, :256 * 256 * 3].reshape(F, 256, 256, 3).contiguous()
+        depth = torch.zeros(F, 256, 256, device=dev)
+        poses = torch.zeros(F, 12, dtype=torch.float64)
+        del local_buf
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = sdist.gather_scene_map(rgb, depth, poses)
+        torch.cuda.synchronize()
+        full_s = max_over_ranks(time.perf_counter() - t0, world)
+        total = world * F * rec
+        allgather = {"bytes_per_rank": int(F * rec), "frames_per_rank": F, "ms": ag_ms, "delivered": bool(ok),
+                     "algbw_GBps": total / (ag_ms * 1e-3) / 1e9, "busbw_GBps": total * (world - 1) / world / (ag_ms * 1e-3) / 1e9,
+                     "gather_scene_map_s": full_s, "frames_gathered": int(got[0].shape[0]),
+                     "note": "all_gather_into_tensor of the packed per-frame records (uint8 RGB + fp32 depth + f64 pose) at "
+                             "BASELINE.json configs[3]'s size: 64 trajectories x 399 frames over 8 GPUs = 1.46 GB per rank; "
+                             "gather_scene_map_s adds the count exchange, packing and unpacking"}
+        del got, rgb, depth
 
     if rank == 0:
-        cfg = workload_config(args, world)
-        cfg["cuda_graph"] = graph is not None
+        cfg = workload_config(ds, res, B, world)
+        cfg["cuda_graph"] = h.graph is not None
         cfg["sources_per_frame"] = int(N)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (tensor-core products as 3-term split bf16, fp32 accumulate)", "data": "synthetic", "config": cfg, "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "dtype": "f32 (tensor-core products as 3-term split bf16, fp32 accumulate)", "data": "synthetic", "config": cfg,
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h.h2d), "d2h_bytes_per_step": int(h.d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "api": "VQModel.get_x + VQModel.forward(topk=1) + frame_outputs, pinned host buffers"},
-            "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"kernel": "tc_gemm_kernel (tcgen05 implicit-GEMM conv + attention products)", "bound": "tensor",
-                         "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": conv_tflops / peaks["tflops"],
-                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": gemm_alg_bytes,
-                         "peak_source": peaks["source"] + ", sustained bf16",
-                         "launches_per_step": len(gemm_events), "share_of_step": conv_ms / (ms / args.steps),
-                         "flops_per_step": conv_flops_total, "mma_issue_tflops": conv_tflops * nsplit,
-                         "frac_mma_issue": conv_tflops * nsplit / peaks["tflops"],
-                         "note": "achieved counts ALGORITHMIC flops (2*M*N*K of the fp32 conv / attention products); every "
-                                 "product is issued as 3 bf16 MMAs (hi*hi + hi*lo + lo*hi) to stay within 1e-3 of the fp32 "
-                                 "reference, so the tensor pipe runs at mma_issue_tflops"},
+            "gpu_launches": h.launches_per_step * args.steps, "gpu_launches_per_step": h.launches_per_step,
+            "roofline": roof,
             "kernels": {
                 "splat": {"bound": "hbm", "ms": splat_ms, "achieved": splat_bytes / (splat_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                           "unit": "GB/s", "frac": splat_bytes / (splat_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "bytes": splat_bytes},
@@ -497,19 +724,27 @@ def main():
                        "canonical_fp32_kernel_ms": vq_simt_ms,
                        "note": "2*T*n_e*D flops dominate the 21 MB of traffic at T=2048 tokens: the search runs on the tensor pipe "
                                "(tile minima) + exact canonical re-evaluation of the candidate tiles"},
-                "tc_gemm_ms_per_step": conv_ms},
+                "tc_gemm_ms_per_step": roof["ms_per_step"]},
         }
         if single is not None:
             line["single_trajectory"] = single
-        if scene_loop is not None:
-            line["scene_loop"] = scene_loop
+        if loop_rec is not None:
+            line["scene_loop"] = loop_rec
         if traj_batch is not None:
             line["trajectory_batch"] = traj_batch
-        if ag_ms is not None:
-            line["allgather_ms"] = ag_ms
-            line["allgather_bytes_per_rank"] = int(B * sdist.record_bytes(res, res))
+            configs["configs[3]"] = dict(traj_batch)
+            if allgather is not None:
+                configs["configs[3]"]["allgather"] = allgather
+        if allgather is not None:
+            line["allgather_ms"] = allgather["ms"]
+            line["allgather_bytes_per_rank"] = allgather["bytes_per_rank"]
+            line["allgather_busbw_GBps"] = allgather["busbw_GBps"]
+        if rank_identity is not None:
+            line["rank_identity"] = rank_identity
+        if configs:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
-            fps, n, dt = cpu_reference_fps(model.state_dict(), batch_np, ds, min_seconds=10.0, max_frames=8)
+            fps, n, dt = cpu_reference_fps(model.state_dict(), h.batch_np, ds, min_seconds=10.0, max_frames=8)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{n} frames of the same workload at batch 1 in {dt:.1f} s (torch CPU fp32 oracle port, "
                                               f"{os.cpu_count()} threads; the reference hard-codes batch 1)"}

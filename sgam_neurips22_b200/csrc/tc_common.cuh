@@ -20,14 +20,38 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done;
+}
+// Bounded wait: a protocol bug (a missing arrive, a wrong parity, a tx-count that never completes) used to be a silent
+// hang of the whole GPU box.  After SGAM_MBAR_TIMEOUT_NS of wall time (%globaltimer, sampled every 4096 polls, so the
+// fast path costs nothing) the waiter reports which barrier / parity / role was stuck and traps: the launch fails with
+// cudaErrorLaunchFailure and the host sees an error instead of a time-out.
+#ifndef SGAM_MBAR_TIMEOUT_NS
+#define SGAM_MBAR_TIMEOUT_NS 4000000000ull
+#endif
+static __device__ __noinline__ void mbar_timeout_report(uint32_t bar_addr, uint32_t parity) {
+    printf("sgam: mbarrier wait timed out: block %d thread %d (warp %d) barrier smem 0x%x parity %u\n", (int)blockIdx.x,
+           (int)threadIdx.x, (int)(threadIdx.x >> 5), bar_addr, parity);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spins & 0xfffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > SGAM_MBAR_TIMEOUT_NS) mbar_timeout_report(smem_u32(bar), parity);
+        }
+    }
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
     asm volatile(

@@ -143,8 +143,10 @@ vq_refine_kernel(const float *__restrict__ z, const float *__restrict__ E, const
     m = fminf(fminf(red_f[0], red_f[1]), fminf(red_f[2], red_f[3]));
     const float zzt = zz[t];
     const float thr = m + slack_rel * (zzt + ee_max);
+    // NaN-safe: a NaN / inf latent makes every tile minimum (and thr) NaN or inf; `!(x > thr)` then keeps EVERY tile, so
+    // such a row is re-evaluated exhaustively and gets exactly the canonical kernel's answer instead of an empty list
     for (int i = tid; i < n_tiles; i += VQ_TILE)
-        if (tilemin[(size_t)t * n_tiles + i] <= thr) cand[atomicAdd(&n_cand, 1)] = i;
+        if (!(tilemin[(size_t)t * n_tiles + i] > thr)) cand[atomicAdd(&n_cand, 1)] = i;
     __syncthreads();
     unsigned long long key = ~0ull;
     const int nc = n_cand;
@@ -169,7 +171,8 @@ vq_refine_kernel(const float *__restrict__ z, const float *__restrict__ E, const
     __syncthreads();
     key = red_k[0];
     for (int w = 1; w < 4; ++w) key = red_k[w] < key ? red_k[w] : key;
-    const unsigned e = (unsigned)(key & 0xffffffffull);
+    unsigned e = (unsigned)(key & 0xffffffffull);
+    if (e >= (unsigned)(n_tiles * VQ_TILE)) e = 0;     // cannot happen with the NaN-safe candidate test; never index out of the codebook
     if (tid == 0) {
         idx[t] = (int64_t)e;
         if (dmin) dmin[t] = orderable_float((uint32_t)(key >> 32));

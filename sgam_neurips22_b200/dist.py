@@ -20,9 +20,9 @@ def record_bytes(H, W):
 
 def pack_records(rgb_u8, depth, poses):
     """rgb_u8 [F,H,W,3] uint8, depth [F,H,W] fp32, poses [F,12] float64 -> [F, record_bytes] uint8 (same device)."""
-    F = rgb_u8.shape[0]
-    return torch.cat([rgb_u8.reshape(F, -1), depth.contiguous().view(torch.uint8).reshape(F, -1),
-                      poses.to(rgb_u8.device).contiguous().view(torch.uint8).reshape(F, -1)], dim=1).contiguous()
+    F, H, W = depth.shape
+    return torch.cat([rgb_u8.reshape(F, H * W * 3), depth.contiguous().view(torch.uint8).reshape(F, H * W * 4),
+                      poses.to(rgb_u8.device).contiguous().view(torch.uint8).reshape(F, POSE_BYTES)], dim=1).contiguous()
 
 
 def unpack_records(buf, H, W):
@@ -35,15 +35,27 @@ def unpack_records(buf, H, W):
 
 
 def gather_scene_map(rgb_u8, depth, poses, group=None):
-    """All ranks contribute the same number of frames F; returns (rgb [world*F,...], depth, poses) ordered by rank.
-    A single all_gather_into_tensor over NVLink / NVSwitch (gloo on CPU)."""
+    """Every rank contributes its F_r frames (F_r may differ between ranks and may be 0: `shard` gives unequal counts
+    whenever the trajectory count is not a multiple of the world size); returns (rgb [sum F_r,...], depth, poses)
+    ordered by rank.  The frame counts are exchanged first (one 8-byte all-gather), the records are padded to the largest
+    count, ONE all_gather_into_tensor moves them over NVLink / NVSwitch (gloo on CPU), and the padding is dropped."""
     H, W = depth.shape[-2:]
     local = pack_records(rgb_u8, depth, poses)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return unpack_records(local, H, W)
     world = dist.get_world_size(group)
-    out = torch.empty((world * local.shape[0], local.shape[1]), dtype=torch.uint8, device=local.device)
+    counts = torch.empty(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(counts, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device), group=group)
+    counts = [int(c) for c in counts.tolist()]
+    fmax = max(counts)
+    if fmax == 0:
+        return unpack_records(local, H, W)
+    if local.shape[0] < fmax:
+        local = torch.cat([local, local.new_zeros(fmax - local.shape[0], local.shape[1])])
+    out = torch.empty((world * fmax, local.shape[1]), dtype=torch.uint8, device=local.device)
     dist.all_gather_into_tensor(out, local, group=group)
+    if any(c != fmax for c in counts):
+        out = torch.cat([out[r * fmax:r * fmax + c] for r, c in enumerate(counts)])
     return unpack_records(out, H, W)
 
 

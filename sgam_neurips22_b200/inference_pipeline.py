@@ -100,17 +100,12 @@ class InfiniteSceneGeneration:
         self.image_resolution = tuple(int(v) for v in image_resolution)
         if self.image_resolution[0] % 16 or self.image_resolution[1] % 16:
             raise ValueError("image_resolution must be a multiple of 16 (the VQGAN down-samples by 16)")
-        self.output_dim = ((20, 20) if data == "clevr-infinite" else (100, 1)) if output_dim is None else output_dim
+        self.output_dim = self.default_output_dim(data) if output_dim is None else output_dim
         is_vq = isinstance(dynamic_model, VQModel)
+        self.K = self.intrinsics_for(data, self.image_resolution)
         if data == "clevr-infinite":
-            self.K = np.array([[355.5555, 0, 128], [0, 355.5555, 128], [0, 0, 1]])            # :61-65 (for 256x256)
-            self.K[0] = self.K[0] * self.image_resolution[1] / 256
-            self.K[1] = self.K[1] * self.image_resolution[0] / 256
             self.num_src = (5 if num_src is None else num_src) if is_vq else 1                 # :68
         else:
-            self.K = np.array([[497.77774, 0, 256], [0, 497.77774, 256], [0, 0, 1]])          # :83-89
-            self.K[0] = self.K[0] * self.image_resolution[1] / 512
-            self.K[1] = self.K[1] * self.image_resolution[0] / 512
             self.num_src = (3 if num_src is None else num_src) if is_vq else 1                 # :90
         self.K_inv = np.linalg.inv(self.K)
         self.curr = 1
@@ -139,6 +134,21 @@ class InfiniteSceneGeneration:
         if self.use_rgbd_integration and tsdf_depth_fn is None:
             self._init_volume()
 
+    @staticmethod
+    def default_output_dim(data):
+        return (20, 20) if data == "clevr-infinite" else (100, 1)
+
+    @staticmethod
+    def intrinsics_for(data, image_resolution=(256, 256)):
+        """:61-65 (CLEVR, given for 256x256) and :83-89 (GoogleEarth, given for 512x512), scaled to the working resolution."""
+        if data == "clevr-infinite":
+            K, base = np.array([[355.5555, 0, 128], [0, 355.5555, 128], [0, 0, 1]]), 256
+        else:
+            K, base = np.array([[497.77774, 0, 256], [0, 497.77774, 256], [0, 0, 1]]), 512
+        K[0] = K[0] * image_resolution[1] / base
+        K[1] = K[1] * image_resolution[0] / base
+        return K
+
     # ------------------------------------------------------------------------------------ seed / files
     def _stage_seed(self, template_root, seed_frame):
         """Recreate the output directory from the templates (:37-54) and return the seed frame (uint8 RGB at the
@@ -158,11 +168,21 @@ class InfiniteSceneGeneration:
         else:
             os.makedirs(out, exist_ok=True)
             img_fn = sorted(Path(f"{template_root}/google_earth/seed{self.seed_index}").glob("im*"))[0]
-            shutil.copy(img_fn, out / img_fn.name.replace(".png", "_00_00.png"))
-            shutil.copy(str(img_fn).replace("im", "dm").replace(".png", ".npy"),
-                        out / img_fn.name.replace("im", "dm").replace(".png", "_00_00.npy"))
+            stem = img_fn.name[len("im"):-len(".png")]                       # "_00000"
+            shutil.copy(img_fn, out / f"im{stem}_00_00.png")
+            shutil.copy(img_fn.with_name(f"dm{stem}.npy"), out / f"dm{stem}_00_00.npy")
         dm_file = sorted(out.glob("dm_*_00_00.npy"))[0]
-        return self._load_rgb(str(dm_file).replace("dm", "im").replace("npy", "png")), np.load(dm_file)
+        return self._load_rgb(self._sibling(dm_file, "im", ".png")), np.load(dm_file)
+
+    @staticmethod
+    def _sibling(path, prefix, suffix=None):
+        """`<dir>/<old prefix>_<rest>.<ext>` -> `<dir>/<prefix>_<rest><suffix>`: the reference derives its file names by
+        str.replace on a relative path (e.g. :191); here roots are configurable, so only the NAME is rewritten."""
+        path = Path(path)
+        rest = path.name[path.name.index("_"):]
+        if suffix is not None:
+            rest = rest[:rest.rindex(".")] + suffix
+        return path.with_name(prefix + rest)
 
     @staticmethod
     def _save_png(path, rgb):
@@ -188,7 +208,7 @@ class InfiniteSceneGeneration:
         known = {}
         for f in Path(self.grid_transform_path).glob("dm*"):
             parts = f.name[3:-4].split("_")
-            known[(int(parts[1]), int(parts[2]))] = {"rgb_path": str(f).replace("dm", "im").replace("npy", "png"),
+            known[(int(parts[1]), int(parts[2]))] = {"rgb_path": str(self._sibling(f, "im", ".png")),
                                                      "depth_path": str(f), "orig_frame_idx": int(parts[0])}
         return known
 
@@ -278,7 +298,8 @@ class InfiniteSceneGeneration:
         f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
         batch = {"Ks": f32(np.stack([self.K] * N))[None], "K_invs": f32(np.stack([np.linalg.inv(self.K)] * N))[None],
                  "R_rels": f32(np.stack(R_rels))[None], "t_rels": f32(np.stack(t_rels))[None],
-                 "dst_img": torch.zeros(1, H, W, 3), "dst_depth": torch.zeros(1, H, W),
+                 "dst_img": self._dst_zeros(H, W)[0], "dst_depth": self._dst_zeros(H, W)[1],       # :596-597 placeholders
+                 "_dst_placeholder": True,                  # tells VQModel.get_x not to code the (all-zero) target frame
                  "src_imgs": src_imgs, "src_depths": src_depths}
         if self.use_rgbd_integration:
             first = tuple(self._ordered_grid_coords[0])                     # the seed's second ray->z conversion happens
@@ -290,6 +311,12 @@ class InfiniteSceneGeneration:
             batch["warped_tgt_features"] = warped[None]
             batch["warped_tgt_depth"] = tgt_depth[None]
         return batch
+
+    def _dst_zeros(self, H, W):
+        z = getattr(self, "_dst_zero_cache", None)
+        if z is None or z[0].shape[1:3] != (H, W):
+            z = self._dst_zero_cache = (torch.zeros(1, H, W, 3), torch.zeros(1, H, W))
+        return z
 
     def inverse_warping(self, src_imgs, src_depths, tgt_depth, src_intrinsics, tgt_intrinsic, T_tgt2srcs,
                         padding_mode='zeros', depth_threshold=100, as_numpy=True):
@@ -428,9 +455,9 @@ class InfiniteSceneGeneration:
         for R_path in sorted(self.grid_transform_path.glob("R_*_*_*.npy")):
             Rt = np.eye(4)
             Rt[:3, :3] = np.load(str(R_path))
-            Rt[:3, 3] = np.load(str(R_path).replace("R", "t"))
-            depth = np.load(str(R_path).replace("R", "dm"))
-            color = np.array(Image.open(str(R_path).replace("R", "im").replace("npy", "png")).convert("RGB"))
+            Rt[:3, 3] = np.load(str(self._sibling(R_path, "t")))
+            depth = np.load(str(self._sibling(R_path, "dm")))
+            color = np.array(Image.open(str(self._sibling(R_path, "im", ".png"))).convert("RGB"))
             p, c = self.prepare_pcd(depth, color, self.K, Rt)
             pts.append(p)
             cols.append(c)

@@ -30,7 +30,17 @@ def _get(cfg, key, default=None):
 
 
 def _plain(cfg):
-    if hasattr(cfg, "to_container"):
+    """Config -> plain dict / list.  The real OmegaConf is detected explicitly: under the reference-pinned
+    omegaconf==2.0.0 a DictConfig answers None for ANY missing attribute, so duck-typing on `to_container` would call
+    None; with omegaconf >= 2.1 it raises.  Only the built-in ConfigNode shim has a `to_container` method."""
+    try:
+        from omegaconf import OmegaConf as _OC  # noqa: WPS433 (optional dependency, absent from the target image)
+        if _OC.is_config(cfg):
+            return _OC.to_container(cfg, resolve=True)
+    except ImportError:
+        pass
+    from .config import ConfigNode
+    if isinstance(cfg, ConfigNode):
         return cfg.to_container()
     if isinstance(cfg, dict):
         return {k: _plain(v) for k, v in cfg.items()}
@@ -215,9 +225,12 @@ class VQModel(torch.nn.Module):
                                     channels_last=channels_last, policy=self.splat_policy)
             x, mask = out["x"], out["mask"]
         extrapolation_mask = mask.view(torch.bool)
+        # model.py:238: the coded target frame.  The scene loop feeds all-zero placeholders (inference_pipeline.py:596-597)
+        # and never reads x_dst; its batches carry "_dst_placeholder" so that the per-frame path stays free of ATen work.
         x_dst = None
-        if not return_extrapolation_mask:                                       # training-style call: ground-truth side
+        if "dst_img" in batch and "dst_depth" in batch and not batch.get("_dst_placeholder", False):
             x_dst = self._x_dst(batch, dataset)
+        if not return_extrapolation_mask:
             return x, x_dst
         return x, x_dst, extrapolation_mask, x[:, 3:4]
 

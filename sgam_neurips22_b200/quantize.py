@@ -14,7 +14,12 @@ class VectorQuantizer2(torch.nn.Module):
         self.n_e, self.e_dim, self.beta, self.legacy = n_e, e_dim, beta, legacy
         self.sane_index_shape = sane_index_shape
         self.embedding = torch.nn.Embedding(n_e, e_dim)
-        self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)            # quantize.py:233
+        self.kmean_init_codebook_path = kmean_init_codebook_path
+        if kmean_init_codebook_path is None:
+            self.embedding.weight.data.uniform_(-1.0 / n_e, 1.0 / n_e)        # quantize.py:231-233
+        else:
+            import numpy as np
+            self.embedding.weight.data.copy_(torch.from_numpy(np.load(kmean_init_codebook_path)))     # quantize.py:234-235
         self.embedding.weight.requires_grad_(False)
 
     def _nearest(self, z):

@@ -32,7 +32,11 @@ class TrajectoryBatch:
         self.ids = sdist.shard(len(seed_frames), rank, world_size)
         self.pipes = [InfiniteSceneGeneration(dynamic_model, data, seed_frame=seed_frames[t], seed_index=t,
                                               output_root=output_root, **pipeline_kwargs) for t in self.ids]
-        self.n_steps = self.pipes[0].output_dim[0] * self.pipes[0].output_dim[1] - 1 if self.pipes else 0
+        # a rank may own no trajectory (fewer trajectories than ranks): it still takes part in gather_map
+        self.image_resolution = tuple(pipeline_kwargs.get("image_resolution", (256, 256)))
+        self.K = InfiniteSceneGeneration.intrinsics_for(data, self.image_resolution)
+        dim = pipeline_kwargs.get("output_dim") or InfiniteSceneGeneration.default_output_dim(data)
+        self.n_steps = dim[0] * dim[1] - 1
 
     @torch.no_grad()
     def step(self, save_res_to_disk=False):
@@ -49,7 +53,7 @@ class TrajectoryBatch:
             n_src = {b["src_depths"].shape[1] for b in batches}
             if len(n_src) != 1:
                 raise RuntimeError(f"trajectories of one micro-batch must select the same number of sources, got {sorted(n_src)}")
-            batch = {k: torch.cat([b[k] for b in batches], 0) for k in batches[0]}
+            batch = {k: (torch.cat([b[k] for b in batches], 0) if torch.is_tensor(batches[0][k]) else batches[0][k]) for k in batches[0]}
             batch["src_depths"] = batch["src_depths"][..., None]                                   # :870
             x, _, mask, _ = self.model.get_x(batch, self.data, return_extrapolation_mask=True, no_depth_range=True, parallel=True)
             decs, _, _, _ = self.model(x, topk=chunk[0].topk, extrapolation_mask=mask, get_pre_quantized_feature=True,
@@ -72,6 +76,11 @@ class TrajectoryBatch:
         """Compact records of every local frame in (trajectory, zig-zag) order: uint8 RGB [F,H,W,3], fp32 depth
         [F,H,W], float64 poses [F,12] (R row-major, t).  The seed frame's depth is the one the splat path uses."""
         rgbs, depths, poses = [], [], []
+        if not self.pipes:
+            H, W = self.image_resolution
+            dev = self.model.device
+            return (torch.empty(0, H, W, 3, dtype=torch.uint8, device=dev), torch.empty(0, H, W, device=dev),
+                    torch.empty(0, 12, dtype=torch.float64))
         for p in self.pipes:
             for c in p._ordered_grid_coords[:p.curr]:
                 rgb, d = p._frames[tuple(c)]
@@ -85,5 +94,5 @@ class TrajectoryBatch:
         """The job's fused map on every rank: one all_gather_into_tensor of the records (NCCL over NVLink), then
         `unproject_records` (prepare_pcd, :1014-1036).  Returns (xyz float64 [P,3], rgb [P,3] in [0,1], records)."""
         rgb, depth, poses = sdist.gather_scene_map(*self.local_records(), group=group)
-        xyz, col = sdist.unproject_records(rgb, depth, poses.to(depth.device), self.pipes[0].K)
+        xyz, col = sdist.unproject_records(rgb, depth, poses.to(depth.device), self.K)
         return xyz, col, (rgb, depth, poses)

@@ -141,6 +141,63 @@ def test_final_map_allgather_world2_gloo():
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _records(r, F, H=8, W=6):
+    g = torch.Generator().manual_seed(100 + r)
+    return (torch.randint(0, 256, (F, H, W, 3), generator=g, dtype=torch.uint8), torch.rand(F, H, W, generator=g),
+            torch.rand(F, 12, generator=g, dtype=torch.float64))
+
+
+def _gloo_uneven_worker(rank, world, port, q):
+    """shard() hands out unequal frame counts when trajectories % world != 0 and none at all to surplus ranks."""
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from sgam_neurips22_b200 import dist as sdist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    counts = [3, 0, 2][:world]
+    all_rgb, all_depth, all_poses = sdist.gather_scene_map(*_records(rank, counts[rank]))
+    exp = [_records(r, counts[r]) for r in range(world)]
+    ok = torch.equal(all_rgb, torch.cat([e[0] for e in exp])) and torch.equal(all_depth, torch.cat([e[1] for e in exp])) \
+        and torch.equal(all_poses, torch.cat([e[2] for e in exp])) and all_rgb.shape[0] == sum(counts)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_final_map_allgather_uneven_counts_and_an_empty_rank_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_uneven_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True), (2, True)]
+
+
+def test_plain_config_conversion_does_not_duck_type_omegaconf():
+    """under omegaconf 2.0 `hasattr(cfg, "to_container")` is True and the attribute is None."""
+    from sgam_neurips22_b200.config import ConfigNode, _wrap
+    from sgam_neurips22_b200.model import _plain
+
+    class FakeDictConfig(dict):                       # answers None for every missing attribute, like DictConfig 2.0
+        def __getattr__(self, k):
+            return None
+    assert _plain(FakeDictConfig(ch=128, ch_mult=[1, 2])) == {"ch": 128, "ch_mult": [1, 2]}
+    node = _wrap({"a": {"b": [1, {"c": 2}]}})
+    assert isinstance(node, ConfigNode) and _plain(node) == {"a": {"b": [1, {"c": 2}]}}
+
+
+def test_file_names_are_derived_from_the_name_not_the_directory(tmp_path):
+    """str.replace over the whole path rewrote directories containing 'R', 'dm', 'im' or 'npy'."""
+    from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration as ISG
+    d = tmp_path / "RESULTS_dm_im.npy_dir"
+    assert ISG._sibling(d / "R_00003_01_02.npy", "t") == d / "t_00003_01_02.npy"
+    assert ISG._sibling(d / "R_00003_01_02.npy", "im", ".png") == d / "im_00003_01_02.png"
+    assert ISG._sibling(d / "dm_00000_00_00.npy", "im", ".png") == d / "im_00000_00_00.png"
+
+
 def test_unproject_records_matches_prepare_pcd():
     from oracle import native
     from sgam_neurips22_b200 import dist as sdist
