@@ -13,7 +13,8 @@ import sys
 import numpy as np
 import pytest
 
-from tests.fixtures import dropin
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures"))
+import dropin  # noqa: E402  (tests/fixtures/dropin.py)
 
 pytestmark = pytest.mark.gpu
 
