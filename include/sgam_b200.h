@@ -216,6 +216,14 @@ long long sgam_tc_gn_partial_floats(int B, int Ho, int Wo);
 int sgam_groupnorm_split_fused(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
                                float *gn_partial, int B, int Ho, int Wo, int C, int swish, void *stream);
 
+/* Fused single-head self-attention of a 256-channel AttnBlock (diffusionmodules/model.py:168-192: bmm(q,k) * C^-0.5,
+ * softmax over keys, bmm(v, w^T)) as ONE flash-style kernel: scores and probabilities live in tensor memory, the
+ * [B,T,T] matrix is never written.  q, k: [B,T,C] split bf16; vt = V^T [B,C,T] split bf16 (so that P.V is an A.B^T
+ * product with K-major operands); o: [B,T,C] split bf16 (the proj_out conv's operand).  Needs C == 256, T % 256 == 0. */
+int sgam_attention_tc_supported(int B, int T, int C);
+int sgam_attention_tc(const void *q_hi, const void *q_lo, const void *k_hi, const void *k_lo, const void *vt_hi,
+                      const void *vt_lo, void *o_hi, void *o_lo, int B, int T, int C, float scale, void *stream);
+
 /* Batched C = alpha * A . B^T (+ bias_m[row]) on tensor cores.  A [batch|1, M, K], B [batch|1, N, K] split-bf16
  * (a_batched / b_batched say whether the operand has the batch dimension); output fp32 C and/or split-bf16. */
 int sgam_gemm_nt_tc(const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo, const float *bias_m,

@@ -27,6 +27,7 @@ SOURCES = {
     "net_tc.cu": [],
     "net_tc2.cu": [],
     "net_tc3.cu": [],
+    "net_attn.cu": [],
     "net_tc_prep.cu": [],
 }
 

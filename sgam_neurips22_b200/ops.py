@@ -473,3 +473,23 @@ def gemm_nt_tc(a, b, bias_m=None, alpha=1.0, out_f32=True, out_split=False, nspl
     if out_f32 and out_split:
         return y, pair
     return y if out_f32 else pair
+
+
+def attention_tc_supported(B, T, C):
+    return bool(_lib.load().sgam_attention_tc_supported(B, T, C))
+
+
+def attention_tc(q, k, vT, scale):
+    """Fused softmax(q . k^T * scale) . v on tcgen05 (AttnBlock, diffusionmodules/model.py:168-192): the [B,T,T] scores
+    never leave the SM.  q, k = (hi, lo) [B,T,C]; vT = (hi, lo) [B,C,T]; returns o = (hi, lo) [B,T,C]."""
+    lib = _lib.load()
+    for n, t in (("q_hi", q[0]), ("q_lo", q[1]), ("k_hi", k[0]), ("k_lo", k[1]), ("vT_hi", vT[0]), ("vT_lo", vT[1])):
+        _chk(t, torch.bfloat16, n)
+    B, T, C = q[0].shape
+    if tuple(k[0].shape) != (B, T, C) or tuple(vT[0].shape) != (B, C, T):
+        raise RuntimeError(f"attention_tc: shapes q {tuple(q[0].shape)} k {tuple(k[0].shape)} vT {tuple(vT[0].shape)}")
+    o = _bf16_pair((B, T, C), q[0].device)
+    _lib.check(lib.sgam_attention_tc(q[0].data_ptr(), q[1].data_ptr(), k[0].data_ptr(), k[1].data_ptr(), vT[0].data_ptr(),
+                                     vT[1].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), B, T, C, float(scale), _stream()),
+               "sgam_attention_tc")
+    return o

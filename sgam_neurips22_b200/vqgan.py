@@ -131,9 +131,13 @@ class VQGANEngine:
             # V^T [B, C, T] = W_v . h^T + b_v (bias per row), so that P.V is another A.B^T product
             vT = ops.gemm_nt_tc(self.wsplit[f"{name}.v"], flat(hs, (B, T, C)), bias_m=self.p[f"{name}.v.bias"],
                                 out_f32=False, out_split=True, nsplit=self.nsplit)
-            s = ops.gemm_nt_tc(flat(q, (B, T, C)), flat(k, (B, T, C)), alpha=scale, nsplit=self.nsplit)    # [B, T, T] fp32
-            p = ops.softmax_split(s)
-            o = ops.gemm_nt_tc(p, vT, out_f32=False, out_split=True, nsplit=self.nsplit)                    # [B, T, C]
+            if self.use_fused_attention(B, T, C):
+                # one flash-style kernel: scores / probabilities stay in tensor memory, [B,T,T] is never written
+                o = ops.attention_tc(flat(q, (B, T, C)), flat(k, (B, T, C)), vT, scale)
+            else:
+                s = ops.gemm_nt_tc(flat(q, (B, T, C)), flat(k, (B, T, C)), alpha=scale, nsplit=self.nsplit)    # [B, T, T] fp32
+                p = ops.softmax_split(s)
+                o = ops.gemm_nt_tc(p, vT, out_f32=False, out_split=True, nsplit=self.nsplit)                    # [B, T, C]
             return self.conv_tc(f"{name}.proj_out", flat(o, (B, H, W, C)), 1, residual=x)
         h_ = self.norm(f"{name}.norm", x, False)
         q = self.conv(f"{name}.q", h_, ksize=1).view(B, T, C)
@@ -143,6 +147,16 @@ class VQGANEngine:
         ops.softmax_rows_(s)
         o = ops.gemm_nt(s, vT).view(B, H, W, C)
         return self.conv(f"{name}.proj_out", o, ksize=1, residual=x)
+
+    def use_fused_attention(self, B, T, C):
+        """The fused kernel works on 256-query pair tiles, one per cluster: it needs enough of them to fill the machine
+        (at one trajectory a 4096-token block is 16 tiles on 74 SM pairs -- there the three-pass path, which spreads
+        the score matrix over every SM, is faster).  SGAM_ATTN=fused|3pass overrides the choice (tests, experiments)."""
+        import os
+        mode = os.environ.get("SGAM_ATTN", "auto")
+        if mode == "3pass" or self.nsplit != 3 or not ops.attention_tc_supported(B, T, C):
+            return False
+        return mode == "fused" or B * (T // 256) >= 48
 
     # ------------------------------------------------------------------ encoder / decoder
     def encoder(self, h):

@@ -1,0 +1,108 @@
+"""The fused (flash-style) attention kernel of the 256-channel AttnBlocks, through the C ABI.
+Reference: sgam/generative_sensing_module/modules/diffusionmodules/model.py:168-192 -- w = softmax(q^T k * C^-0.5) over the
+keys, h = v w^T -- evaluated in float64 by plain torch ops.  Tolerance: 5e-5 rel-L2 (3-term split-bf16 products with fp32
+accumulation, fp32 online softmax), the same bar as the other tensor-core unit ops; the whole-network bars (tokens
+identical, decoded RGB-D < 1e-3) are held in test_gpu_tc.py / test_gpu_bench_configs.py with this kernel in the path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from sgam_neurips22_b200 import ops as _ops
+    return _ops
+
+
+def reference(q, k, v, scale):
+    s = torch.einsum("btc,bsc->bts", q.double(), k.double()) * scale
+    return torch.einsum("bts,bsc->btc", torch.softmax(s, dim=-1), v.double())
+
+
+def run(ops, q, k, v, scale):
+    qs, ks = ops.split_weight(q), ops.split_weight(k)
+    vts = ops.split_weight(v.transpose(1, 2).contiguous())
+    oh, ol = ops.attention_tc(qs, ks, vts, scale)
+    torch.cuda.synchronize()
+    return oh.float() + ol.float()
+
+
+# (B, T): one pair tile; two key tiles; ragged cluster count; > 74 pair tiles (persistent loop, O hand-over); config-5 length
+@pytest.mark.parametrize("B,T", [(1, 256), (2, 512), (3, 1024), (1, 4096), (8, 4096), (1, 16384)])
+def test_fused_attention_matches_float64(ops, B, T):
+    C = 256
+    g = torch.Generator(device="cuda").manual_seed(B * 100003 + T)
+    q = torch.randn(B, T, C, generator=g, device="cuda")
+    k = torch.randn(B, T, C, generator=g, device="cuda")
+    v = torch.randn(B, T, C, generator=g, device="cuda") * 2 + 0.5
+    scale = C ** -0.5
+    assert ops.attention_tc_supported(B, T, C)
+    out = run(ops, q, k, v, scale)
+    ref = reference(q, k, v, scale)
+    assert tuple(out.shape) == (B, T, C) and rel(out, ref) < 5e-5
+    # per-row accuracy too (a wrong row-sum or a dropped key tile shows up in single rows, not in the global norm)
+    row_err = ((out.double() - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item()
+    assert row_err < 5e-4, row_err
+    assert torch.equal(out, run(ops, q, k, v, scale)), "fused attention must be deterministic"
+
+
+def test_fused_attention_growing_maxima_exercise_the_o_correction(ops):
+    """Keys ordered so that every key tile raises the row maxima by far more than the lazy-rescale threshold (2^8): O and
+    the row sums are corrected in tensor memory at every tile.  Peaked rows (softmax ~ one-hot) and flat rows mixed."""
+    B, T, C = 2, 1024, 256
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q = torch.randn(B, T, C, generator=g, device="cuda")
+    k = torch.randn(B, T, C, generator=g, device="cuda")
+    ramp = torch.linspace(0.2, 6.0, T, device="cuda")[None, :, None]                # later keys -> much larger scores
+    k = k * ramp + q.mean(dim=1, keepdim=True) * ramp * 2
+    q[:, ::7] *= 0.01                                                                # nearly flat rows
+    v = torch.randn(B, T, C, generator=g, device="cuda")
+    scale = C ** -0.5
+    s = torch.einsum("btc,bsc->bts", q.double(), k.double()) * scale
+    tile_max = s.view(B, T, T // 128, 128).amax(-1)
+    assert ((tile_max[..., 1:] - tile_max[..., :-1].cummax(-1).values) * 1.4427 > 8).any(), "the case must trigger the correction"
+    out = run(ops, q, k, v, scale)
+    ref = reference(q, k, v, scale)
+    assert rel(out, ref) < 5e-5
+    assert ((out.double() - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item() < 5e-4
+
+
+def test_fused_attention_equals_three_pass_path_in_the_engine(ops):
+    """AttnBlock through the engine with SGAM_ATTN=fused vs SGAM_ATTN=3pass (QK^T GEMM, softmax pass, PV GEMM)."""
+    from oracle import recipes
+    from sgam_neurips22_b200.vqgan import VQGANEngine
+    sd = recipes.make_state_dict(recipes.DATASETS["google_earth"]["n_embed"], seed=0)
+    eng = VQGANEngine(sd, recipes.DDCONFIG, "cuda:0", mode="tc")
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 32, 32, 256, generator=g).cuda()                              # 1024 tokens
+    name = "encoder.down.2.attn.0"
+    old = os.environ.get("SGAM_ATTN")
+    try:
+        os.environ["SGAM_ATTN"] = "fused"
+        y_f = eng.attn_block(name, x)
+        os.environ["SGAM_ATTN"] = "3pass"
+        y_3 = eng.attn_block(name, x)
+    finally:
+        if old is None:
+            os.environ.pop("SGAM_ATTN", None)
+        else:
+            os.environ["SGAM_ATTN"] = old
+    assert rel(y_f, y_3) < 2e-5
+
+
+def test_unsupported_shapes_are_refused(ops):
+    assert not ops.attention_tc_supported(1, 256, 512) and not ops.attention_tc_supported(1, 384, 256)
+    q = ops.split_weight(torch.randn(1, 384, 256, device="cuda"))
+    vt = ops.split_weight(torch.randn(1, 256, 384, device="cuda"))
+    with pytest.raises(RuntimeError):
+        ops.attention_tc(q, q, vt, 0.0625)
