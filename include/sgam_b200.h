@@ -234,15 +234,20 @@ int sgam_gemm_nt_tc(const void *a_hi, const void *a_lo, const void *b_hi, const 
  * RGB-D integration (use_rgbd_integration=True).  Replaces InfiniteSceneGeneration.rgbd_integration
  * (sgam/inference_pipeline.py:745-838) and volume.extract_point_cloud() (:446-447), i.e. the reference's calls into
  * open3d==0.15.2 (ScalableTSDFVolume :119-131, integrate :777, extract_triangle_mesh :786,
- * OffscreenRenderer.render_to_depth_image :825).  The unit hash becomes a DENSE grid of 16^3-voxel units over the box
- * [o*, o*+n*) (unit indices; unit i covers world [i*16*voxel_length, (i+1)*16*voxel_length)); the target depth is
- * ray-cast from the volume instead of meshed and rasterised (parity with Open3D is unpinned).
+ * OffscreenRenderer.render_to_depth_image :825).  The unit hash becomes a PAGE TABLE over the grid of 16^3-voxel units
+ * of the box [o*, o*+n*) (unit indices; unit i covers world [i*16*voxel_length, (i+1)*16*voxel_length)) in front of a
+ * pool of unit blocks; the target depth is ray-cast from the volume instead of meshed and rasterised (parity
+ * with Open3D is unpinned).
  *   stamp [nx*ny*nz] u32: 0 = never opened, else the `frame` counter of the unit's last integration (zero it once)
- *   vol   [units][4096][2] fp32 (tsdf, weight), zero-initialised; color [units][4096][3] fp32 (0..255) or NULL
+ *   page  [nx*ny*nz] i32: 0 = no block, else 1 + the unit's block in the pool (zero it once)
+ *   pool_state [3] i32: blocks handed out (may run past the capacity), capacity in blocks (set by the caller), units
+ *                 dropped because the pool was full (zero [0] and [2] once)
+ *   vol   [capacity][4096][2] fp32 (tsdf, weight), zero-initialised; color [capacity][4096][3] fp32 (0..255) or NULL
  *   unit (ux,uy,uz) -> (uz*ny + uy)*nx + ux ; voxel (lx,ly,lz) -> (lx*16 + ly)*16 + lz
  *   host_* pointers are HOST memory: row-major 3x4 poses and K = {fx, fy, cx, cy}; they are copied into the launch.
  */
-size_t sgam_tsdf_volume_bytes(int nx, int ny, int nz, int with_color);
+size_t sgam_tsdf_volume_bytes(int nx, int ny, int nz, int with_color);      /* bytes of a pool that holds EVERY unit of the box */
+size_t sgam_tsdf_block_bytes(int with_color);                               /* bytes of one pool block */
 /* one RGB-D frame: depth [H,W] (>= depth_trunc or <= 0 ignored), rgb [H,W,3] fp32 in [-1,1] (uint8 lattice) or NULL;
  * opens the units within sdf_trunc of every `stride`-th depth sample (host_cam2world, fp64) and integrates them
  * (host_world2cam, fp32).  frame must be non-zero and distinct per call; work [1 + nx*ny*nz] i32 scratch (the
@@ -250,17 +255,18 @@ size_t sgam_tsdf_volume_bytes(int nx, int ny, int nz, int with_color);
 int sgam_tsdf_integrate(const float *depth, const float *rgb, int H, int W, const double *host_cam2world,
                         const float *host_world2cam, const double *host_K, int stride, float depth_trunc,
                         int ox, int oy, int oz, int nx, int ny, int nz, float voxel_length, float sdf_trunc,
-                        uint32_t *stamp, uint32_t frame, int *work, float *vol, float *color, void *stream);
+                        uint32_t *stamp, uint32_t frame, int *work, int *page, int *pool_state, float *vol, float *color,
+                        void *stream);
 /* view-space z of the first + -> - crossing along the ray of pixel (u + pixel_center, v + pixel_center); 0 = no surface.
  * Samples every step_vox voxel lengths of z in [z_near, z_far], skipping never-opened units.  out [H,W]. */
-int sgam_tsdf_raycast(const uint32_t *stamp, const float *vol, int ox, int oy, int oz, int nx, int ny, int nz,
+int sgam_tsdf_raycast(const int *page, const float *vol, int ox, int oy, int oz, int nx, int ny, int nz,
                       float voxel_length, float sdf_trunc, const float *host_cam2world, const double *host_K,
                       float pixel_center, int H, int W, float z_near, float z_far, float step_vox, float *out,
                       void *stream);
 /* zero-crossing point cloud.  Pass 1 (unit_offsets NULL): unit_counts[unit] = crossings in the unit.  Pass 2:
  * unit_offsets = exclusive prefix sum of the counts; xyz [n,3], rgb [n,3] in [0,1] are written in (unit, lx, ly, lz,
  * axis) order -- deterministic. */
-int sgam_tsdf_extract(const uint32_t *stamp, const float *vol, const float *color, int ox, int oy, int oz,
+int sgam_tsdf_extract(const int *page, const float *vol, const float *color, int ox, int oy, int oz,
                       int nx, int ny, int nz, float voxel_length, float sdf_trunc, long long *unit_counts,
                       const long long *unit_offsets, float *xyz, float *rgb, void *stream);
 

@@ -58,8 +58,9 @@ SIGNATURES = {
     "sgam_attention_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
     "sgam_unproject_points": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     "sgam_tsdf_volume_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
+    "sgam_tsdf_block_bytes": (c_sz, [c_i]),
     "sgam_tsdf_integrate": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f,
-                                  c_p, c_u32, c_p, c_p, c_p, c_p]),
+                                  c_p, c_u32, c_p, c_p, c_p, c_p, c_p, c_p]),
     "sgam_tsdf_raycast": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_f, c_i, c_i, c_f, c_f, c_f,
                                 c_p, c_p]),
     "sgam_tsdf_extract": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p]),

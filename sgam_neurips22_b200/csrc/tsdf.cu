@@ -5,10 +5,12 @@
 // (ScalableTSDFVolume.integrate / extract_triangle_mesh / OffscreenRenderer.render_to_depth_image).  The arithmetic
 // follows the published algorithm of that version (see oracle/csrc/tsdf_oracle.c, to which these kernels are
 // bit-exact); the B200 re-design is
-//   * a DENSE grid of 16^3-voxel units in HBM (a few GB of the 180 GB) instead of a host-side hash of units: a unit
-//     is "opened" by stamping it (the first stamper queues it on the frame's work list), every unit is one contiguous
-//     32 KB block swept by one CTA with fully coalesced 8-byte accesses, no allocation, no host round trip,
-//     deterministic results;
+//   * a PAGE TABLE over the dense grid of 16^3-voxel units of the reachable box (4 bytes per unit) in front of a POOL of
+//     unit blocks in HBM, instead of a host-side hash of units: a unit is "opened" by stamping it (the first stamper of a
+//     frame queues it on the frame's work list and, the first time ever, takes the next pool block with one integer
+//     atomic), every unit is one contiguous 32 KB (+ 48 KB colour) block swept by one CTA with fully coalesced 8-byte
+//     accesses, no host round trip, and results that do not depend on which block a unit got (round 1 kept the whole
+//     box dense: 7-15 GB per GoogleEarth trajectory; the pool holds only the units near observed surfaces);
 //   * the target depth is ray-cast straight from the volume (one thread per pixel, trilinear samples, empty units
 //     skipped) instead of marching cubes + mesh upload + rasterisation every step.
 // All three kernels are HBM / L2 latency bound integer-and-fp32 work; compiled with --fmad=false so that every
@@ -34,9 +36,11 @@ __device__ __forceinline__ long long unit_index(const Grid &g, int ux, int uy, i
 }
 
 // ScalableTSDFVolume::Integrate, first half: one thread per strided depth sample opens the units around its point.
+// pool_state: [0] blocks handed out so far (may run past the capacity), [1] capacity, [2] units dropped for lack of blocks
 __global__ void __launch_bounds__(256)
 tsdf_touch_kernel(const float *__restrict__ depth, int H, int W, Pose34d c2w, Intr K, int stride, float depth_trunc,
-                  Grid g, uint32_t *__restrict__ stamp, uint32_t frame, int *__restrict__ work) {
+                  Grid g, uint32_t *__restrict__ stamp, uint32_t frame, int *__restrict__ work, int *__restrict__ page,
+                  int *__restrict__ pool_state) {
     const int sw = (W + stride - 1) / stride, sh = (H + stride - 1) / stride;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= sw * sh) return;
@@ -59,8 +63,17 @@ tsdf_touch_kernel(const float *__restrict__ depth, int H, int W, Pose34d c2w, In
                 const long long u = unit_index(g, ux, uy, uz);
                 if (u < 0) continue;
                 // the first thread to stamp a unit this frame queues it; the list order varies from run to run but the
-                // units are disjoint, so the result does not
-                if (atomicExch(stamp + u, frame) != frame) work[1 + atomicAdd(work, 1)] = (int)u;
+                // units are disjoint, so the result does not.  Exactly one thread per (unit, frame) gets here, so the
+                // page entry needs no atomic; which pool block a unit receives varies, its contents do not.
+                if (atomicExch(stamp + u, frame) != frame) {
+                    int pg = page[u];
+                    if (pg == 0) {
+                        const int slot = atomicAdd(pool_state, 1);
+                        if (slot < pool_state[1]) page[u] = pg = slot + 1;
+                        else atomicAdd(pool_state + 2, 1);                 // pool exhausted: the unit stays closed
+                    }
+                    if (pg > 0) work[1 + atomicAdd(work, 1)] = (int)u;
+                }
             }
 }
 
@@ -71,8 +84,8 @@ tsdf_touch_kernel(const float *__restrict__ depth, int H, int W, Pose34d c2w, In
 // step); each thread replays its lz additions so that the rounding is the same.
 __global__ void __launch_bounds__(256)
 tsdf_integrate_kernel(const float *__restrict__ depth, const float *__restrict__ rgb, int H, int W, Pose34f w2c, Intr Kd,
-                      float depth_trunc, Grid g, const int *__restrict__ work, float2 *__restrict__ vol,
-                      float *__restrict__ color) {
+                      float depth_trunc, Grid g, const int *__restrict__ work, const int *__restrict__ page,
+                      float2 *__restrict__ vol, float *__restrict__ color) {
     const int n_open = work[0];
     const float fx = (float)Kd.fx, fy = (float)Kd.fy, cx = (float)Kd.cx, cy = (float)Kd.cy;
     const float inv_fx = 1.0f / fx, inv_fy = 1.0f / fy;
@@ -82,6 +95,7 @@ tsdf_integrate_kernel(const float *__restrict__ depth, const float *__restrict__
     const float inc[3] = {w2c.m[2] * vl, w2c.m[6] * vl, w2c.m[10] * vl};
     for (int k = blockIdx.x; k < n_open; k += gridDim.x) {
         const long long u = work[1 + k];
+        const long long blk = page[u] - 1;                          // pool block of the unit (queued units always have one)
         const int ux = (int)(u % g.nx) + g.ox, uy = (int)((u / g.nx) % g.ny) + g.oy, uz = (int)(u / ((long long)g.nx * g.ny)) + g.oz;
         const float p0y = half + vl * (float)ly + (float)uy * unit_len, p0z = half + (float)uz * unit_len;
         for (int lx = 0; lx < RES; ++lx) {
@@ -105,7 +119,7 @@ tsdf_integrate_kernel(const float *__restrict__ depth, const float *__restrict__
             const float sdf = (d - pc[2]) * mult;
             if (!(sdf > -trunc)) continue;
             const float tsdf = fminf(1.0f, sdf * trunc_inv);
-            const size_t v = (size_t)u * UNIT_VOX + (size_t)lx * (RES * RES) + threadIdx.x;
+            const size_t v = (size_t)blk * UNIT_VOX + (size_t)lx * (RES * RES) + threadIdx.x;
             float2 fw = vol[v];
             const float w = fw.y;
             fw.x = (fw.x * w + tsdf) / (w + 1.0f);
@@ -122,17 +136,18 @@ tsdf_integrate_kernel(const float *__restrict__ depth, const float *__restrict__
     }
 }
 
-__device__ __forceinline__ float2 fetch(const Grid &g, const uint32_t *__restrict__ stamp, const float2 *__restrict__ vol,
+__device__ __forceinline__ float2 fetch(const Grid &g, const int *__restrict__ page, const float2 *__restrict__ vol,
                                         int gx, int gy, int gz) {
     const long long u = unit_index(g, gx >> 4, gy >> 4, gz >> 4);
-    if (u < 0 || stamp[u] == 0) return make_float2(0.0f, 0.0f);
-    return __ldg(vol + (size_t)u * UNIT_VOX + (((gx & 15) * RES) + (gy & 15)) * RES + (gz & 15));
+    const int pg = u < 0 ? 0 : __ldg(page + u);
+    if (pg <= 0) return make_float2(0.0f, 0.0f);
+    return __ldg(vol + (size_t)(pg - 1) * UNIT_VOX + (((gx & 15) * RES) + (gy & 15)) * RES + (gz & 15));
 }
 
 // Target depth by ray casting; one thread per pixel, 8x8 pixel tiles (a warp = 8x4 pixels) so that neighbouring rays
 // share voxels in L1/L2 and diverge little.
 __global__ void __launch_bounds__(64)
-tsdf_raycast_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__restrict__ vol, Pose34f c2w, Intr Kd,
+tsdf_raycast_kernel(Grid g, const int *__restrict__ page, const float2 *__restrict__ vol, Pose34f c2w, Intr Kd,
                     float pixel_center, int H, int W, float z_near, float z_far, float step_vox, float *__restrict__ out) {
     const int u = blockIdx.x * 8 + (threadIdx.x & 7), v = blockIdx.y * 8 + (threadIdx.x >> 3);
     if (u >= W || v >= H) return;
@@ -156,7 +171,8 @@ tsdf_raycast_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__
         const float fl[3] = {floorf(p[0]), floorf(p[1]), floorf(p[2])};
         const int b[3] = {(int)fl[0], (int)fl[1], (int)fl[2]};
         const long long unit = unit_index(g, b[0] >> 4, b[1] >> 4, b[2] >> 4);
-        if (unit < 0 || stamp[unit] == 0) {
+        const int pg = unit < 0 ? 0 : __ldg(page + unit);
+        if (pg <= 0) {
             float t_exit = INFINITY;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -176,12 +192,12 @@ tsdf_raycast_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__
         float2 fw[8];
         const int l0 = b[0] & 15, l1 = b[1] & 15, l2 = b[2] & 15;
         if (l0 < 15 && l1 < 15 && l2 < 15) {
-            const float2 *cell = vol + (size_t)unit * UNIT_VOX + ((l0 * RES) + l1) * RES + l2;
+            const float2 *cell = vol + (size_t)(pg - 1) * UNIT_VOX + ((l0 * RES) + l1) * RES + l2;
 #pragma unroll
             for (int c = 0; c < 8; ++c) fw[c] = __ldg(cell + (c & 1) * RES * RES + ((c >> 1) & 1) * RES + (c >> 2));
         } else {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) fw[c] = fetch(g, stamp, vol, b[0] + (c & 1), b[1] + ((c >> 1) & 1), b[2] + (c >> 2));
+            for (int c = 0; c < 8; ++c) fw[c] = fetch(g, page, vol, b[0] + (c & 1), b[1] + ((c >> 1) & 1), b[2] + (c >> 2));
         }
         float f = 0.0f;
         bool valid = true;
@@ -210,20 +226,20 @@ tsdf_raycast_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__
 // ScalableTSDFVolume::ExtractPointCloud.  offsets == nullptr: counts[unit] = number of crossings of the unit;
 // otherwise write them at offsets[unit] in (lx, ly, lz, axis) order (block-wide exclusive scan).
 __global__ void __launch_bounds__(256)
-tsdf_extract_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__restrict__ vol, const float *__restrict__ color,
+tsdf_extract_kernel(Grid g, const int *__restrict__ page, const float2 *__restrict__ vol, const float *__restrict__ color,
                     long long *__restrict__ counts, const long long *__restrict__ offsets, float *__restrict__ xyz,
                     float *__restrict__ rgb) {
     __shared__ int scan[256];
     const long long u = blockIdx.x;
-    const bool open = stamp[u] != 0;
-    if (!open) {                                    // uniform per CTA
+    const long long blk = page[u] - 1;
+    if (blk < 0) {                                    // uniform per CTA
         if (!offsets && threadIdx.x == 0) counts[u] = 0;
         return;
     }
     const float vl = g.voxel_length, half = vl * 0.5f, unit_len = vl * RES;
     const int ux = (int)(u % g.nx) + g.ox, uy = (int)((u / g.nx) % g.ny) + g.oy, uz = (int)(u / ((long long)g.nx * g.ny)) + g.oz;
     const int lx = threadIdx.x >> 4, ly = threadIdx.x & 15;
-    const size_t base = (size_t)u * UNIT_VOX + (size_t)(lx * RES + ly) * RES;
+    const size_t base = (size_t)blk * UNIT_VOX + (size_t)(lx * RES + ly) * RES;
     for (int pass = offsets ? 0 : 1; pass < 2; ++pass) {
         // pass 0 (fill mode only): count, then scan; pass 1: count (count mode) or write (fill mode)
         const bool write = offsets && pass == 1;
@@ -241,8 +257,9 @@ tsdf_extract_kernel(Grid g, const uint32_t *__restrict__ stamp, const float2 *__
             for (int ax = 0; ax < 3; ++ax) {
                 const int g1x = g0[0] + (ax == 0), g1y = g0[1] + (ax == 1), g1z = g0[2] + (ax == 2);
                 const long long u1 = unit_index(g, g1x >> 4, g1y >> 4, g1z >> 4);
-                if (u1 < 0 || stamp[u1] == 0) continue;
-                const size_t v1 = (size_t)u1 * UNIT_VOX + (((g1x & 15) * RES) + (g1y & 15)) * RES + (g1z & 15);
+                const long long blk1 = u1 < 0 ? -1 : (long long)page[u1] - 1;
+                if (blk1 < 0) continue;
+                const size_t v1 = (size_t)blk1 * UNIT_VOX + (((g1x & 15) * RES) + (g1y & 15)) * RES + (g1z & 15);
                 const float2 fw1 = vol[v1];
                 const float f1 = fw1.x;
                 if (!(fw1.y != 0.0f && f1 < 0.98f && f1 >= -0.98f && f0 * f1 < 0.0f)) continue;
@@ -292,12 +309,14 @@ int check_grid(const char *what, int nx, int ny, int nz, float voxel_length, flo
 extern "C" size_t sgam_tsdf_volume_bytes(int nx, int ny, int nz, int with_color) {
     return (size_t)nx * ny * nz * UNIT_VOX * (with_color ? 5 : 2) * sizeof(float);
 }
+extern "C" size_t sgam_tsdf_block_bytes(int with_color) { return (size_t)UNIT_VOX * (with_color ? 5 : 2) * sizeof(float); }
 
 extern "C" int sgam_tsdf_integrate(const float *depth, const float *rgb, int H, int W, const double *host_cam2world,
                                    const float *host_world2cam, const double *host_K, int stride, float depth_trunc,
                                    int ox, int oy, int oz, int nx, int ny, int nz, float voxel_length, float sdf_trunc,
-                                   uint32_t *stamp, uint32_t frame, int *work, float *vol, float *color, void *stream) {
-    SGAM_REQUIRE(depth && host_cam2world && host_world2cam && host_K && stamp && work && vol, "tsdf_integrate: null pointer");
+                                   uint32_t *stamp, uint32_t frame, int *work, int *page, int *pool_state, float *vol, float *color,
+                                   void *stream) {
+    SGAM_REQUIRE(depth && host_cam2world && host_world2cam && host_K && stamp && work && page && pool_state && vol, "tsdf_integrate: null pointer");
     SGAM_REQUIRE(H > 0 && W > 0 && stride > 0 && frame != 0, "tsdf_integrate: bad H/W/stride, or frame stamp 0");
     SGAM_REQUIRE((color == nullptr) == (rgb == nullptr), "tsdf_integrate: rgb and color go together");
     if (int rc = check_grid("tsdf_integrate", nx, ny, nz, voxel_length, sdf_trunc)) return rc;
@@ -307,38 +326,38 @@ extern "C" int sgam_tsdf_integrate(const float *depth, const float *rgb, int H, 
     for (int i = 0; i < 12; ++i) { c2w.m[i] = host_cam2world[i]; w2c.m[i] = host_world2cam[i]; }
     const int samples = ((W + stride - 1) / stride) * ((H + stride - 1) / stride);
     SGAM_CUDA_OK(cudaMemsetAsync(work, 0, sizeof(int), s));
-    tsdf_touch_kernel<<<cdiv(samples, 256), 256, 0, s>>>(depth, H, W, c2w, K, stride, depth_trunc, g, stamp, frame, work);
+    tsdf_touch_kernel<<<cdiv(samples, 256), 256, 0, s>>>(depth, H, W, c2w, K, stride, depth_trunc, g, stamp, frame, work, page, pool_state);
     SGAM_LAUNCH_OK();
-    tsdf_integrate_kernel<<<148 * 4, 256, 0, s>>>(depth, rgb, H, W, w2c, K, depth_trunc, g, work, reinterpret_cast<float2 *>(vol), color);
+    tsdf_integrate_kernel<<<148 * 4, 256, 0, s>>>(depth, rgb, H, W, w2c, K, depth_trunc, g, work, page, reinterpret_cast<float2 *>(vol), color);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
 
-extern "C" int sgam_tsdf_raycast(const uint32_t *stamp, const float *vol, int ox, int oy, int oz, int nx, int ny, int nz,
+extern "C" int sgam_tsdf_raycast(const int *page, const float *vol, int ox, int oy, int oz, int nx, int ny, int nz,
                                  float voxel_length, float sdf_trunc, const float *host_cam2world, const double *host_K,
                                  float pixel_center, int H, int W, float z_near, float z_far, float step_vox, float *out,
                                  void *stream) {
-    SGAM_REQUIRE(stamp && vol && host_cam2world && host_K && out, "tsdf_raycast: null pointer");
+    SGAM_REQUIRE(page && vol && host_cam2world && host_K && out, "tsdf_raycast: null pointer");
     SGAM_REQUIRE(H > 0 && W > 0 && step_vox > 0.0f && z_far >= z_near && z_near >= 0.0f, "tsdf_raycast: bad H/W/step/z range");
     if (int rc = check_grid("tsdf_raycast", nx, ny, nz, voxel_length, sdf_trunc)) return rc;
     Grid g{ox, oy, oz, nx, ny, nz, voxel_length, sdf_trunc};
     Pose34f c2w; Intr K{host_K[0], host_K[1], host_K[2], host_K[3]};
     for (int i = 0; i < 12; ++i) c2w.m[i] = host_cam2world[i];
     tsdf_raycast_kernel<<<dim3(cdiv(W, 8), cdiv(H, 8)), 64, 0, (cudaStream_t)stream>>>(
-        g, stamp, reinterpret_cast<const float2 *>(vol), c2w, K, pixel_center, H, W, z_near, z_far, step_vox, out);
+        g, page, reinterpret_cast<const float2 *>(vol), c2w, K, pixel_center, H, W, z_near, z_far, step_vox, out);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
 
-extern "C" int sgam_tsdf_extract(const uint32_t *stamp, const float *vol, const float *color, int ox, int oy, int oz,
+extern "C" int sgam_tsdf_extract(const int *page, const float *vol, const float *color, int ox, int oy, int oz,
                                  int nx, int ny, int nz, float voxel_length, float sdf_trunc, long long *unit_counts,
                                  const long long *unit_offsets, float *xyz, float *rgb, void *stream) {
-    SGAM_REQUIRE(stamp && vol, "tsdf_extract: null pointer");
+    SGAM_REQUIRE(page && vol, "tsdf_extract: null pointer");
     SGAM_REQUIRE(unit_offsets ? (xyz && rgb) : (unit_counts != nullptr), "tsdf_extract: count pass needs unit_counts, fill pass needs xyz and rgb");
     if (int rc = check_grid("tsdf_extract", nx, ny, nz, voxel_length, sdf_trunc)) return rc;
     Grid g{ox, oy, oz, nx, ny, nz, voxel_length, sdf_trunc};
     tsdf_extract_kernel<<<(unsigned)((long long)nx * ny * nz), 256, 0, (cudaStream_t)stream>>>(
-        g, stamp, reinterpret_cast<const float2 *>(vol), color, unit_counts, unit_offsets, xyz, rgb);
+        g, page, reinterpret_cast<const float2 *>(vol), color, unit_counts, unit_offsets, xyz, rgb);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }

@@ -5,8 +5,8 @@ RGB8)), :745-838 rgbd_integration (integrate the selected source frames, extract
 render_to_depth_image(z_in_view_space=True), inf -> 0) and :446-447 (volume.extract_point_cloud()).
 
 `TSDFVolume` keeps Open3D's method names (`integrate`, `extract_point_cloud`) and adds `render_depth`, which stands
-for the mesh-extraction + off-screen-render pair.  The volume is a dense grid of 16^3-voxel units over a fixed world
-box, resident in HBM (see csrc/tsdf.cu); PyTorch only owns the memory.  Parity with Open3D itself is unpinned
+for the mesh-extraction + off-screen-render pair.  The volume is a page table over the 16^3-voxel units of a fixed world
+box in front of a pool of unit blocks, all resident in HBM (see csrc/tsdf.cu); PyTorch only owns the memory.  Parity with Open3D itself is unpinned
 (third-party binary, absent here); the kernels are bit-exact to the oracle restatement of its published algorithm.
 """
 import ctypes
@@ -34,14 +34,17 @@ def frustum_box(K, world2cams, H, W, z_far, pad):
 
 
 class TSDFVolume:
-    """Dense-unit TSDF volume on one GPU.
+    """Paged TSDF volume on one GPU.
 
-    voxel_length, sdf_trunc: as ScalableTSDFVolume (:119-131).  box_min / box_max: world-space bounds of the dense
-    grid; surface samples outside it are dropped (Open3D's hash is unbounded -- size the box from the trajectory with
-    `frustum_box`).  with_color keeps the RGB8 running average needed only by extract_point_cloud()."""
+    voxel_length, sdf_trunc: as ScalableTSDFVolume (:119-131).  box_min / box_max: world-space bounds of the unit grid;
+    surface samples outside it are dropped (Open3D's hash is unbounded -- size the box from the trajectory with
+    `frustum_box`).  Only the page table (12 bytes per unit of the box) is dense; voxel data lives in a pool of
+    `max_bytes` (default 2 GiB) worth of unit blocks that are handed out the first time a unit is opened, so the
+    footprint follows the observed surface, not the box.  If the pool runs out, further units stay closed and
+    `dropped_units()` reports them.  with_color keeps the RGB8 running average needed only by extract_point_cloud()."""
 
     def __init__(self, voxel_length, sdf_trunc, box_min, box_max, device="cuda:0", with_color=True,
-                 depth_sampling_stride=4, max_bytes=64 << 30):
+                 depth_sampling_stride=4, max_bytes=2 << 30):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("TSDFVolume lives on a CUDA device (no CPU fallback)")
@@ -53,15 +56,46 @@ class TSDFVolume:
         self.origin = tuple(int(v) for v in lo)
         self.dims = tuple(int(v) for v in (hi - lo + 1))
         lib = _lib.load()
-        need = lib.sgam_tsdf_volume_bytes(*self.dims, int(with_color))
-        if need > max_bytes:
-            raise MemoryError(f"TSDF grid {self.dims} units needs {need / 2**30:.1f} GiB (> max_bytes); shrink the box")
         n = self.dims[0] * self.dims[1] * self.dims[2]
+        if n >= 1 << 31:
+            raise MemoryError(f"TSDF grid {self.dims} has too many units for the 32-bit page table; shrink the box")
+        self.capacity = int(max(1, min(n, max_bytes // lib.sgam_tsdf_block_bytes(int(with_color)))))
         self.stamp = torch.zeros(n, dtype=torch.int32, device=self.device)           # u32 on the device side
-        self.vol = torch.zeros(n, UNIT_RES ** 3, 2, device=self.device)
-        self.color = torch.zeros(n, UNIT_RES ** 3, 3, device=self.device) if with_color else None
+        self.page = torch.zeros(n, dtype=torch.int32, device=self.device)            # 0 = closed, else 1 + pool block
+        self.pool_state = torch.tensor([0, self.capacity, 0], dtype=torch.int32, device=self.device)
+        self.pool_vol = torch.zeros(self.capacity, UNIT_RES ** 3, 2, device=self.device)
+        self.pool_color = torch.zeros(self.capacity, UNIT_RES ** 3, 3, device=self.device) if with_color else None
         self.work = torch.zeros(n + 1, dtype=torch.int32, device=self.device)        # per-frame list of opened units
         self.frame = 0
+
+    # ---- bookkeeping (these synchronise; not used on the per-frame path)
+    def memory_bytes(self):
+        t = [self.stamp, self.page, self.pool_state, self.pool_vol, self.work] + ([self.pool_color] if self.pool_color is not None else [])
+        return sum(x.numel() * x.element_size() for x in t)
+
+    def units_in_use(self):
+        return min(int(self.pool_state[0].item()), self.capacity)
+
+    def dropped_units(self):
+        return int(self.pool_state[2].item())
+
+    def _dense(self, pool):
+        """Pool -> dense [units, 4096, c] view of the whole box (tests / debugging; refuses boxes above 8 GiB)."""
+        n = self.page.numel()
+        if n * pool.shape[1] * pool.shape[2] * 4 > 8 << 30:
+            raise MemoryError("dense view of this box is too large; index the pool through `page`")
+        dense = torch.zeros(n, pool.shape[1], pool.shape[2], device=self.device)
+        opened = self.page > 0
+        dense[opened] = pool[(self.page[opened] - 1).long()]
+        return dense
+
+    @property
+    def vol(self):
+        return self._dense(self.pool_vol)
+
+    @property
+    def color(self):
+        return None if self.pool_color is None else self._dense(self.pool_color)
 
     # the grid arguments every entry point takes
     def _grid(self):
@@ -79,7 +113,7 @@ class TSDFVolume:
         lib = _lib.load()
         _chk(depth, name="depth")
         H, W = depth.shape
-        if self.color is None:
+        if self.pool_color is None:
             rgb = None
         if rgb is not None:
             _chk(rgb, name="rgb")
@@ -93,8 +127,9 @@ class TSDFVolume:
         _lib.check(lib.sgam_tsdf_integrate(depth.data_ptr(), None if rgb is None else rgb.data_ptr(), H, W,
                                            c2w.ctypes.data, w2c32.ctypes.data, k4.ctypes.data, self.stride,
                                            ctypes.c_float(depth_trunc), *self._grid(), self.stamp.data_ptr(),
-                                           ctypes.c_uint32(self.frame), self.work.data_ptr(), self.vol.data_ptr(),
-                                           None if rgb is None else self.color.data_ptr(), _stream()), "sgam_tsdf_integrate")
+                                           ctypes.c_uint32(self.frame), self.work.data_ptr(), self.page.data_ptr(),
+                                           self.pool_state.data_ptr(), self.pool_vol.data_ptr(),
+                                           None if rgb is None else self.pool_color.data_ptr(), _stream()), "sgam_tsdf_integrate")
 
     def render_depth(self, K, world2cam, H, W, pixel_center=0.5, z_near=0.05, z_far=20.0, step_vox=0.5):
         """extract_triangle_mesh + OffscreenRenderer.render_to_depth_image(z_in_view_space=True) (:786-827) as one
@@ -103,7 +138,7 @@ class TSDFVolume:
         c2w32 = np.ascontiguousarray(np.linalg.inv(np.asarray(world2cam, np.float64))[:3], np.float32)
         k4 = self._k4(K)
         out = torch.empty(H, W, device=self.device)
-        _lib.check(lib.sgam_tsdf_raycast(self.stamp.data_ptr(), self.vol.data_ptr(), *self._grid(), c2w32.ctypes.data,
+        _lib.check(lib.sgam_tsdf_raycast(self.page.data_ptr(), self.pool_vol.data_ptr(), *self._grid(), c2w32.ctypes.data,
                                          k4.ctypes.data, ctypes.c_float(pixel_center), H, W, ctypes.c_float(z_near),
                                          ctypes.c_float(z_far), ctypes.c_float(step_vox), out.data_ptr(), _stream()),
                    "sgam_tsdf_raycast")
@@ -114,13 +149,13 @@ class TSDFVolume:
         lib = _lib.load()
         n_units = self.stamp.numel()
         counts = torch.empty(n_units, dtype=torch.int64, device=self.device)
-        col = None if self.color is None else self.color.data_ptr()
-        _lib.check(lib.sgam_tsdf_extract(self.stamp.data_ptr(), self.vol.data_ptr(), col, *self._grid(), counts.data_ptr(),
+        col = None if self.pool_color is None else self.pool_color.data_ptr()
+        _lib.check(lib.sgam_tsdf_extract(self.page.data_ptr(), self.pool_vol.data_ptr(), col, *self._grid(), counts.data_ptr(),
                                          None, None, None, _stream()), "sgam_tsdf_extract")
         offsets = torch.cumsum(counts, 0) - counts                       # exclusive prefix sum (plumbing)
         n = int(counts.sum().item())
         xyz, rgb = torch.empty(n, 3, device=self.device), torch.empty(n, 3, device=self.device)
         if n:
-            _lib.check(lib.sgam_tsdf_extract(self.stamp.data_ptr(), self.vol.data_ptr(), col, *self._grid(), counts.data_ptr(),
+            _lib.check(lib.sgam_tsdf_extract(self.page.data_ptr(), self.pool_vol.data_ptr(), col, *self._grid(), counts.data_ptr(),
                                              offsets.data_ptr(), xyz.data_ptr(), rgb.data_ptr(), _stream()), "sgam_tsdf_extract")
         return xyz, rgb
