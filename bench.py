@@ -371,7 +371,7 @@ def latest_traffic():
     return tj["dram_bytes_per_launch"], tj["source"]
 
 
-def scene_loop(model, ds, res, dim, rgbd, world, all_ranks, read_back=False, skip=5):
+def scene_loop(model, ds, res, dim, rgbd, world, all_ranks, read_back=False, skip=5, integrate_once=False):
     """Sequential frames of ONE trajectory per participating rank through InfiniteSceneGeneration.one_step_prediction
     (source selection, pose math, splat or TSDF + inverse warp, forward, uint8 / depth conversion; no disk).  Wall clock
     between device synchronisations, max over the participating ranks.  read_back: every generated frame is also copied
@@ -379,7 +379,7 @@ def scene_loop(model, ds, res, dim, rgbd, world, all_ranks, read_back=False, ski
     from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration
     rank = int(os.environ.get("RANK", 0))
     pipe = InfiniteSceneGeneration(model, ds, seed_frame=synthetic_seed_frame(ds, rank, 256), output_dim=dim,
-                                   use_rgbd_integration=rgbd, image_resolution=(res, res),
+                                   use_rgbd_integration=rgbd, image_resolution=(res, res), integrate_once=integrate_once,
                                    output_root=tempfile.mkdtemp(prefix="sgam_bench_loop_"))
     pin_rgb = torch.empty(res, res, 3, dtype=torch.uint8).pin_memory()
     pin_depth = torch.empty(res, res).pin_memory()
@@ -422,6 +422,7 @@ def _scene_loop_body(pipe, n_loop, skip, all_ranks, world, read_back, pin_rgb, p
     extra = {"h2d_bytes_per_frame": (counted[0] - b0) // max(1, n)}
     if vol is not None and hasattr(vol, "memory_bytes"):
         extra["tsdf_volume_bytes"] = int(vol.memory_bytes())
+        extra["tsdf_units_in_use"], extra["tsdf_units_capacity"], extra["tsdf_units_dropped"] = vol.units_in_use(), vol.capacity, vol.dropped_units()
     return n, dt, extra
 
 
@@ -586,6 +587,7 @@ def main():
             gm = get_model("google_earth")
             n, dt, extra = scene_loop(gm, "google_earth", 256, (60, 1), True, world, all_ranks=False)
             n2, dt2, extra2 = scene_loop(gm, "google_earth", 256, (40, 1), True, world, all_ranks=False, read_back=True)
+            n3, dt3, _ = scene_loop(gm, "google_earth", 256, (60, 1), True, world, all_ranks=False, integrate_once=True)
             h2 = StepHarness(gm, "google_earth", 256, 1, 100, dev, use_graph=not args.no_graph)
             for _ in range(args.warmup):
                 h2.run()
@@ -599,6 +601,10 @@ def main():
                         "d2h_bytes_per_step": 256 * 256 * 7, "frames": n2,
                         "api": "InfiniteSceneGeneration.one_step_prediction(save_res_to_disk=False) + read-back of the frame to "
                                "pinned host memory every step; the frame store itself is device-resident by design"},
+                "integrate_once": {"value": n3 / dt3, "unit": UNIT, "ms_per_frame": 1000.0 * dt3 / n3,
+                                   "note": "flagged deviation (InfiniteSceneGeneration(integrate_once=True)): every frame is fused into the "
+                                           "volume the first time it is selected as a source instead of at every step it is selected "
+                                           "(the reference re-integrates, inference_pipeline.py:771-777)"},
                 "network_step_ms": ms2, "roofline": roof2}
             del h2
         # ---------------- configs[4]: GoogleEarth 512x512, 100-step trajectory, one per GPU on every rank ------------------------
@@ -744,7 +750,7 @@ def main():
         if configs:
             line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
-            fps, n, dt = cpu_reference_fps(model.state_dict(), h.batch_np, ds, min_seconds=10.0, max_frames=8)
+            fps, n, dt = cpu_reference_fps(model.state_dict(), h.batch_np, ds, min_seconds=12.0, max_frames=40)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{n} frames of the same workload at batch 1 in {dt:.1f} s (torch CPU fp32 oracle port, "
                                               f"{os.cpu_count()} threads; the reference hard-codes batch 1)"}

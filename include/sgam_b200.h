@@ -216,6 +216,14 @@ long long sgam_tc_gn_partial_floats(int B, int Ho, int Wo);
 int sgam_groupnorm_split_fused(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
                                float *gn_partial, int B, int Ho, int Wo, int C, int swish, void *stream);
 
+/* Decoder head: decoder.norm_out (GroupNorm(32,128), eps 1e-6) + swish + decoder.conv_out (3x3, 128 -> 4, NCHW output;
+ * diffusionmodules/model.py:534-538) in one exact-fp32 kernel: the normalised halo tile is staged in shared memory once,
+ * the channel reduction runs on the FP32 pipes (a 4-column GEMM tile would waste 97 % of the tensor pipe and re-read the
+ * operand nine times).  x fp32 NHWC [B,H,W,128]; gn_partial = the partial sums sgam_conv2d_tc emitted for x
+ * (sgam_tc_gn_partial_floats(B,H,W) floats); w_t [9][128][4] (tap, input channel, output channel); y [B,4,H,W]. */
+int sgam_gn_head_conv(const float *x, const float *gamma, const float *beta, float *gn_partial, const float *w_t,
+                      const float *bias, float *y, int B, int H, int W, int C, int Cout, void *stream);
+
 /* Fused single-head self-attention of a 256-channel AttnBlock (diffusionmodules/model.py:168-192: bmm(q,k) * C^-0.5,
  * softmax over keys, bmm(v, w^T)) as ONE flash-style kernel: scores and probabilities live in tensor memory, the
  * [B,T,T] matrix is never written.  q, k: [B,T,C] split bf16; vt = V^T [B,C,T] split bf16 (so that P.V is an A.B^T

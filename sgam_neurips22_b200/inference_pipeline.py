@@ -82,7 +82,7 @@ class InfiniteSceneGeneration:
                  dynamic_model, data, topk=1, step_size_denom=2, use_rgbd_integration=False, use_discriminator_loss=False,
                  discriminator_loss_weight=0, recon_on_visible=False, offscreen_rendering=True, output_dim=None, seed_index=0,
                  num_src=None, tsdf_depth_fn=None, template_root="templates", output_root="grid_res", seed_frame=None,
-                 image_resolution=(256, 256)):
+                 image_resolution=(256, 256), integrate_once=False, tsdf_max_bytes=2 << 30):
         self.use_discriminator_loss = use_discriminator_loss
         self.offscreen_rendering = offscreen_rendering
         self.discriminator_loss_weight = discriminator_loss_weight
@@ -94,6 +94,13 @@ class InfiniteSceneGeneration:
         self.dynamic_model = dynamic_model
         self.data = data
         self.tsdf_depth_fn = tsdf_depth_fn
+        # The reference re-integrates EVERY selected source frame at EVERY step (:771-777), so a frame that stays within
+        # the source radius for k steps enters the volume k times (its observations weigh k).  integrate_once=True is a
+        # flagged deviation: each frame is fused the first time it is selected and never again (one integration per
+        # step in steady state instead of num_src, every observation weighs 1).  Default: the reference's behaviour.
+        self.integrate_once = bool(integrate_once)
+        self.tsdf_max_bytes = int(tsdf_max_bytes)
+        self._integrated = set()
         if data not in ("clevr-infinite", "google_earth"):
             raise NotImplementedError                                      # inference_pipeline.py:55-56
         # :42,47 hard-code 256x256; BASELINE.json configs[4] runs GoogleEarth at 512x512, so it is a keyword here
@@ -348,7 +355,7 @@ class InfiniteSceneGeneration:
                 T[:3, :3], T[:3, 3] = node["R"], node["t"]
                 poses.append(T)
         lo, hi = frustum_box(self.K, poses, H, W, self._z_far, pad=trunc + 16 * vox)
-        self.volume = TSDFVolume(vox, trunc, lo, hi, device=self.device, with_color=True)
+        self.volume = TSDFVolume(vox, trunc, lo, hi, device=self.device, with_color=True, max_bytes=self.tsdf_max_bytes)
 
     def rgbd_integration(self, src_nodes, T_tgt, src_depths=None):
         """Integrated target depth [H,W] on the device (:745-838): integrate the selected source frames into the
@@ -358,7 +365,12 @@ class InfiniteSceneGeneration:
             return torch.as_tensor(d).to(self.device, torch.float32).contiguous()
         H, W = self.image_resolution
         for i, n in enumerate(src_nodes):
-            rgb, depth = self._frames[tuple(n["grid_coord"])]
+            key = tuple(n["grid_coord"])
+            if self.integrate_once:
+                if key in self._integrated:
+                    continue
+                self._integrated.add(key)
+            rgb, depth = self._frames[key]
             if src_depths is not None:
                 depth = src_depths[i]
             T_src = np.eye(4)

@@ -493,3 +493,19 @@ def attention_tc(q, k, vT, scale):
                                      vT[1].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), B, T, C, float(scale), _stream()),
                "sgam_attention_tc")
     return o
+
+
+def gn_head_conv(x, gamma, beta, w_t, bias):
+    """decoder.norm_out + swish + decoder.conv_out (diffusionmodules/model.py:534-538) in one fp32 kernel.  x fp32 NHWC
+    [B,H,W,128] carrying the GroupNorm partial sums of its producing conv (`x.gn_partial`); w_t [9,128,4]; -> [B,4,H,W]."""
+    lib = _lib.load()
+    _chk(x, name="x"), _chk(gamma, name="gamma"), _chk(beta, name="beta"), _chk(w_t, name="w_t"), _chk(bias, name="bias")
+    partial = getattr(x, "gn_partial", None)
+    if partial is None:
+        raise RuntimeError("gn_head_conv: x carries no fused GroupNorm statistics (gn_partial)")
+    B, H, W, C = x.shape
+    Cout = w_t.shape[-1]
+    y = torch.empty(B, Cout, H, W, device=x.device)
+    _lib.check(lib.sgam_gn_head_conv(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), partial.data_ptr(), w_t.data_ptr(),
+                                     bias.data_ptr(), y.data_ptr(), B, H, W, C, Cout, _stream()), "sgam_gn_head_conv")
+    return y

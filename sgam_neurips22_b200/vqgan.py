@@ -32,6 +32,8 @@ class VQGANEngine:
         if mode not in ("tc", "simt"):
             raise ValueError(mode)
         self.mode, self.nsplit = mode, nsplit
+        import os
+        self.fused_head = os.environ.get("SGAM_FUSED_HEAD", "1") != "0"
         self.p = {}
         self.wsplit = {}
         self.load_state_dict(state_dict)
@@ -192,6 +194,14 @@ class VQGANEngine:
                     h = self.attn_block(f"decoder.up.{l}.attn.{b}", h)
             if l != 0:
                 h = self.conv_from_f32(f"decoder.up.{l}.upsample.conv", h, 3, upsample=1)
+        w_out = self.p["decoder.conv_out.weight"]
+        if self.mode == "tc" and self.fused_head and getattr(h, "gn_partial", None) is not None and h.shape[-1] == 128 \
+                and w_out.shape == (4, 9 * 128):
+            # GroupNorm + swish + the 4-channel conv as one fp32 kernel (a 4-column GEMM tile wastes the tensor pipe)
+            if "decoder.conv_out.taps" not in self.p:
+                self.p["decoder.conv_out.taps"] = w_out.view(4, 9, 128).permute(1, 2, 0).contiguous()        # [tap, cin, cout]
+            return ops.gn_head_conv(h, self.p["decoder.norm_out.weight"], self.p["decoder.norm_out.bias"],
+                                    self.p["decoder.conv_out.taps"], self.p["decoder.conv_out.bias"])
         if self.tc_ok("decoder.conv_out", h.shape, 3):                          # Cout = 4: zero-padded to one 32-column tile
             return self.conv_tc("decoder.conv_out", self.norm_split("decoder.norm_out", h, True), 3, out_nchw=True)
         h = self.norm("decoder.norm_out", h, True)

@@ -280,3 +280,31 @@ def test_conv2d_tc_split_k(ops, case):
     y = ops.conv2d_tc(xs, ws, bias.cuda(), residual=rr, ksize=ks)
     assert rel(y.permute(0, 3, 1, 2), ref) < 5e-5
     assert torch.equal(y, ops.conv2d_tc(xs, ws, bias.cuda(), residual=rr, ksize=ks))       # deterministic reduction order
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 48), (1, 256, 256), (3, 8, 20), (1, 64, 64)])
+def test_fused_groupnorm_swish_head_conv(ops, shape):
+    """decoder.norm_out + swish + decoder.conv_out (128 -> 4, NCHW) as one fp32 kernel vs GroupNorm / SiLU / conv2d in fp64;
+    ragged tiles (H, W not multiples of the 8 x 16 tile) included."""
+    from sgam_neurips22_b200 import _lib
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = torch.randn(B, 128, H, W, generator=g) * 1.7 + 0.3
+    ga, be = 1 + 0.2 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g)
+    w = torch.randn(4, 128, 3, 3, generator=g) / (128 * 9) ** 0.5
+    bias = torch.randn(4, generator=g)
+    ref = F.group_norm(x.double(), 32, ga.double(), be.double(), eps=1e-6)
+    ref = F.conv2d(ref * torch.sigmoid(ref), w.double(), bias.double(), padding=1)
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    # the statistics layout the conv epilogue emits: [B][tiles][32][sum, sumsq] (+ room for mean / rstd); all in slot 0 here
+    n = _lib.load().sgam_tc_gn_partial_floats(B, H, W)
+    tiles = (n - B * 64) // (B * 64)
+    part = torch.zeros(n)
+    xg = x.double().view(B, 32, 4, H, W)
+    pv = part[:B * tiles * 64].view(B, tiles, 32, 2)
+    pv[:, 0, :, 0] = xg.sum(dim=(2, 3, 4)).float()
+    pv[:, 0, :, 1] = (xg * xg).sum(dim=(2, 3, 4)).float()
+    xn.gn_partial = part.cuda()
+    w_t = w.permute(2, 3, 1, 0).reshape(9, 128, 4).contiguous().cuda()
+    y = ops.gn_head_conv(xn, ga.cuda(), be.cuda(), w_t, bias.cuda())
+    assert tuple(y.shape) == (B, 4, H, W) and rel(y, ref) < 1e-5
