@@ -197,6 +197,15 @@ int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const v
                    int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws,
                    double *splitk_gn_partial, void *stream);
 
+/* Upsample = nearest x2 + 3x3 conv (diffusionmodules/model.py:49-52) in sub-pixel form: each output parity (py, px) is a
+ * 2x2 convolution of the LOW-resolution operand with pre-summed taps.  x_hi/x_lo [B,H,W,Cin] (low resolution);
+ * w_hi/w_lo [4][Cout][4*Cin] (parity 2*py+px; K index (dy*2+dx)*Cin+ci; dy/dx = 0 is the row/column i-1+py / j-1+px);
+ * y [B,2H,2W,Cout] fp32; gn_partial as for sgam_conv2d_tc, sized for the OUTPUT grid.  16/36 of the MMA work of the 3x3
+ * form and no up-sampled operand in HBM. */
+int sgam_conv2d_tc_up2_supported(int B, int H, int W, int Cin, int Cout);
+int sgam_conv2d_tc_up2(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias, float *y,
+                       int B, int H, int W, int Cin, int Cout, int nsplit, float *gn_partial, void *stream);
+
 /* Split-K for under-filled grids (low-resolution layers, single-trajectory batches): when splitk_ws is given and
  * sgam_conv2d_tc_splitk_floats(...) > 0 floats, the K loop is divided among CTAs, partial tiles go to the workspace
  * and a reduce kernel adds them in split order with bias / residual (deterministic; fp32 NHWC output only, no fused

@@ -93,7 +93,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
                     uint8_t *st = smem + (size_t)s * STAGE_BYTES;
                     const int tap = kb / p.kblocks_per_tap, kc = kb - tap * p.kblocks_per_tap;
                     const int kh = tap / p.ks, kw = tap - kh * p.ks;
-                    const int cx = tx * p.BW * p.stride + kw - p.pad, cy = ty * p.BH * p.stride + kh - p.pad;
+                    const int cx = tx * p.BW * p.stride + kw - p.pad + p.shift_x, cy = ty * p.BH * p.stride + kh - p.pad + p.shift_y;
                     mbar_expect_tx(&full_bar[s], tx_bytes);
                     tma_load_4d(st, &mapA_hi, &full_bar[s], kc * BK, cx, cy, ab);
                     tma_load_3d(st + 2 * A_PLANE, &mapB_hi, &full_bar[s], kb * BK, n0, bb);
@@ -443,6 +443,63 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
         return SGAM_OK;
     }
     return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, (cudaStream_t)stream);
+}
+
+// ---- Upsample (nearest x2 + 3x3 conv, diffusionmodules/model.py:49-52) in sub-pixel form ----------------------------
+// Output pixel (2i + py, 2j + px) only sees the 2 x 2 low-resolution neighbourhood rows {i - 1 + py, i + py} x columns
+// {j - 1 + px, j + px}; the nine taps collapse onto it with pre-summed weights (w_hi / w_lo: [4 parities][Cout][4 Cin],
+// parity = 2 py + px, K index = (dy * 2 + dx) * Cin + ci).  Four launches of a 2x2-tap implicit GEMM on the LOW-resolution
+// operand replace one 3x3 launch on a 4x larger up-sampled copy: 16/36 of the MMA work and no up-sampled operand in HBM.
+// H, W: LOW-resolution grid; y [B, 2H, 2W, Cout] fp32; gn_partial sized for the output grid (sgam_tc_gn_partial_floats(B,2H,2W)).
+static int up2_kernel_choice(int B, int H, int W, int Cin, int Cout, int *BN2) {
+    if (Cin % 64 || Cout % 128) return 0;
+    if (swap_applicable(B, H, W, Cin, Cout, 1, true)) return 1;
+    if (tc_use_2cta() && tc2_applicable(B, H, W, Cout, 1, 0, Cout, BN2)) return 2;
+    return 0;
+}
+
+extern "C" int sgam_conv2d_tc_up2_supported(int B, int H, int W, int Cin, int Cout) {
+    int bn = 0;
+    return H > 0 && W > 0 && (H * W) % 128 == 0 && up2_kernel_choice(B, H, W, Cin, Cout, &bn) != 0;
+}
+
+extern "C" int sgam_conv2d_tc_up2(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias, float *y,
+                                  int B, int H, int W, int Cin, int Cout, int nsplit, float *gn_partial, void *stream) {
+    SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && y, "conv2d_tc_up2: null pointer");
+    SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "conv2d_tc_up2: nsplit must be 1 or 3");
+    SGAM_REQUIRE(!gn_partial || (Cout % 128 == 0 && Cout <= 512), "conv2d_tc_up2: fused GroupNorm statistics need Cout in {128,256,384,512}");
+    int BN2 = 0;
+    const int kind = sgam_conv2d_tc_up2_supported(B, H, W, Cin, Cout) ? up2_kernel_choice(B, H, W, Cin, Cout, &BN2) : 0;
+    SGAM_REQUIRE(kind != 0, "conv2d_tc_up2: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
+    const int tiles128 = H * W / 128;                    // GroupNorm partial-sum slots one parity launch fills per image
+    const size_t wplane = (size_t)Cout * 4 * Cin;        // elements of one parity's weight matrix
+    for (int par = 0; par < 4; ++par) {
+        TcParams p{};
+        p.Ho = H; p.Wo = W; p.taps = 4; p.ks = 2; p.pad = 0; p.stride = 1;
+        p.shift_y = (par >> 1) - 1; p.shift_x = (par & 1) - 1; p.up = 1; p.py = par >> 1; p.px = par & 1;
+        p.stat_tiles = 4 * tiles128; p.stat_tile0 = par * tiles128;
+        p.N = Cout; p.n_valid = Cout; p.nsplit = nsplit; p.a_batched = 1; p.b_batched = 0;
+        p.d_batch_stride = 4LL * H * W * Cout; p.alpha = 1.0f; p.bias_n = bias; p.D = y; p.stats = gn_partial; p.cpg = Cout / 32;
+        const __nv_bfloat16 *wh = (const __nv_bfloat16 *)w_hi + par * wplane, *wl = (const __nv_bfloat16 *)w_lo + par * wplane;
+        int rc;
+        if (kind == 1) {
+            rc = launch_conv_swap(x_hi, x_lo, wh, wl, p, B, H, W, Cin, Cout, 2, (cudaStream_t)stream);
+        } else {
+            CUtensorMap a_hi, a_lo, b_hi, b_lo;
+            const int bw = W >= 256 ? 128 : W, bh = W >= 256 ? 1 : 128 / W;
+            const long long adims[4] = {Cin, W, H, B};
+            const int abox[4] = {64, bw, bh, 1};
+            const long long bdims[3] = {4LL * Cin, Cout, 1};
+            const int bbox[3] = {64, BN2 / 2, 1};
+            if ((rc = make_map(&a_hi, x_hi, 4, adims, abox)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox)) ||
+                (rc = make_map(&b_hi, wh, 3, bdims, bbox)) || (rc = make_map(&b_lo, wl, 3, bdims, bbox)))
+                return rc;
+            p.kblocks_per_tap = Cin / 64;
+            rc = launch_tc2(BN2, a_hi, a_lo, b_hi, b_lo, p, B, H, W, Cout, (cudaStream_t)stream);
+        }
+        if (rc) return rc;
+    }
+    return SGAM_OK;
 }
 
 // Workspace (floats) sgam_conv2d_tc wants for split-K on this shape; 0 = the K loop will not be split.

@@ -92,7 +92,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
                     const uint32_t full0 = map_to_cta(&full_bar[s], 0);
                     const int tap = kb / p.kblocks_per_tap, kc = kb - tap * p.kblocks_per_tap;
                     const int kh = tap / p.ks, kw = tap - kh * p.ks;
-                    const int cx = ox0 * p.stride + kw - p.pad, cy = oy0 * p.stride + kh - p.pad;
+                    const int cx = ox0 * p.stride + kw - p.pad + p.shift_x, cy = oy0 * p.stride + kh - p.pad + p.shift_y;
                     if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * tx_bytes);   // the leader alone expects both CTAs' bytes (the
                     tma2_load_4d(st, &mapA_hi, full0, kc * BK, cx, cy, ab);      // tx-count may go negative until it arrives)
                     tma2_load_3d(st + 2 * A_PLANE, &mapB_hi, full0, kb * BK, n0, bb);
@@ -149,7 +149,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             mbar_wait(&tmem_full_bar[acc], (li >> 1) & 1);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            const long long slot = ((long long)b * (g.tiles_x2 * g.tiles_y2) + m2) * 2 + rank;
+            const long long per_img = p.stat_tiles ? p.stat_tiles : 2LL * g.tiles_x2 * g.tiles_y2;
+            const long long slot = (long long)b * per_img + p.stat_tile0 + (long long)m2 * 2 + rank;
             epilogue_rows<BN>(p, tmem_acc, q * 32 + lane, b, oy0, ox0, n0, n_tile, 0, slot, stat_s, epi_stage, q, lane);
             tc_fence_before();
             __syncwarp();

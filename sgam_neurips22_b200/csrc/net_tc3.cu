@@ -92,7 +92,7 @@ tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_co
                     uint8_t *st = smem + (size_t)s * STAGE_BYTES;
                     const int tap = kb / p.kblocks_per_tap, kc = kb - tap * p.kblocks_per_tap;
                     const int kh = tap / p.ks, kw = tap - kh * p.ks;
-                    const int cx = tx * g.BW2 + kw - p.pad, cy = ty * g.BH2 + kh - p.pad;
+                    const int cx = tx * g.BW2 + kw - p.pad + p.shift_x, cy = ty * g.BH2 + kh - p.pad + p.shift_y;
                     mbar_expect_tx(&full_bar[s], tx_bytes);
                     tma_load_3d(st, &mapW_hi, &full_bar[s], kb * BK, n0, 0);
                     tma_load_4d(st + 2 * W_PLANE, &mapP_hi, &full_bar[s], kc * BK, cx, cy, b);
@@ -156,12 +156,14 @@ tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_co
                 uint32_t v[32];
                 tmem_ld32(tmem_acc + (uint32_t)c0, v);
                 const int ly = c0 / g.BW2, lx = c0 - ly * g.BW2;    // BW2 % 32 == 0: the 32 pixels of a chunk share a row
-                const long long m = (long long)(ty * g.BH2 + ly) * p.Wo + (tx * g.BW2 + lx);
+                const int oy = ty * g.BH2 + ly, ox = tx * g.BW2 + lx;
+                const long long m = p.up ? (long long)(2 * oy + p.py) * (2 * p.Wo) + (2 * ox + p.px) : (long long)oy * p.Wo + ox;
                 const long long off = (long long)b * p.d_batch_stride + m * p.N + c;
+                const long long xstep = p.up ? 2LL * p.N : (long long)p.N;     // neighbouring tile pixels: every other output pixel when up
                 float o[32];
                 if (p.R) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = __ldg(p.R + off + (long long)j * p.N);
+                    for (int j = 0; j < 32; ++j) o[j] = __ldg(p.R + off + (long long)j * xstep);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) o[j] += p.alpha * __uint_as_float(v[j]) + bn;
                 } else {
@@ -169,7 +171,7 @@ tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_co
                     for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bn;
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) p.D[off + (long long)j * p.N] = o[j];       // lanes = 32 consecutive channels: one 128-byte line
+                for (int j = 0; j < 32; ++j) p.D[off + (long long)j * xstep] = o[j];     // lanes = 32 consecutive channels: one 128-byte line
                 if (p.stats) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { s_acc += o[j]; q_acc = fmaf(o[j], o[j], q_acc); }
@@ -179,7 +181,8 @@ tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_co
                         if ((lane & (cpg - 1)) == 0) {
                             const int half = c0 >> 7;
                             const int tx128 = g.wide ? 2 * tx + half : tx, ty128 = g.wide ? ty : 2 * ty + half;
-                            const long long slot = (long long)b * g.tiles128 + (long long)ty128 * g.tiles128_x + tx128;
+                            const long long per_img = p.stat_tiles ? p.stat_tiles : g.tiles128;
+                            const long long slot = (long long)b * per_img + p.stat_tile0 + (long long)ty128 * g.tiles128_x + tx128;
                             const int grp = c / cpg;
                             p.stats[(slot * 32 + grp) * 2] = s;
                             p.stats[(slot * 32 + grp) * 2 + 1] = qq;

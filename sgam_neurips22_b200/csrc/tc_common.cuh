@@ -140,6 +140,12 @@ struct TcParams {
     int ksplit, kb_per_split;
     float *splitk_ws;
     long long split_stride;
+    // Sub-pixel form of Upsample (nearest x2, then 3x3 conv; diffusionmodules/model.py:49-52): output parity (py, px) is a
+    // 2x2 convolution of the LOW-resolution tensor with pre-summed taps.  shift_x / shift_y move the tap window
+    // (parity 0 reads rows {i-1, i}, parity 1 rows {i, i+1}); up = 1 scatters tile pixel (oy, ox) to output pixel
+    // (2 oy + py, 2 ox + px) of the 2Ho x 2Wo tensor; the GroupNorm partial sums of the four parity launches share one
+    // buffer: stat_tiles slots per image (0 = this launch's own count), this launch's first slot = stat_tile0.
+    int shift_x, shift_y, up, py, px, stat_tiles, stat_tile0;
 };
 
 // per-warp GroupNorm partial sums of one 32-column chunk: CPG channels per group, rows = lanes
@@ -178,7 +184,8 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
     const int ly = r / p.BW, lx = r - ly * p.BW;
     const int oy = oy0 + ly, ox = ox0 + lx;
     const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
-    const long long m = (long long)oy * p.Wo + ox;          // row within the batch slice
+    const long long m = p.up ? (long long)(2 * oy + p.py) * (2 * p.Wo) + (2 * ox + p.px)      // sub-pixel scatter
+                             : (long long)oy * p.Wo + ox;  // row within the batch slice
     const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
     const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
     float *stg = es.tile[q];

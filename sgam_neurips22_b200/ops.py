@@ -509,3 +509,50 @@ def gn_head_conv(x, gamma, beta, w_t, bias):
     _lib.check(lib.sgam_gn_head_conv(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), partial.data_ptr(), w_t.data_ptr(),
                                      bias.data_ptr(), y.data_ptr(), B, H, W, C, Cout, _stream()), "sgam_gn_head_conv")
     return y
+
+
+def subpixel_weights(w, cin):
+    """Packed 3x3 weights [Cout, 9*Cin] (K index (kh*3+kw)*Cin+ci) -> the four parity matrices of the sub-pixel form of
+    `nearest x2 then conv3x3` [4, Cout, 4*Cin]: parity (py, px), K index (dy*2+dx)*Cin+ci.  Rows: py = 0 reads low-res rows
+    {i-1: kh 0, i: kh 1 + kh 2}; py = 1 reads {i: kh 0 + kh 1, i+1: kh 2}; columns alike.  Taps are summed in fp32."""
+    cout = w.shape[0]
+    w9 = w.view(cout, 3, 3, cin)
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = w.new_zeros(4, cout, 2, 2, cin)
+    for py in (0, 1):
+        for px in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    acc = None
+                    for kh in groups[py][dy]:
+                        for kw in groups[px][dx]:
+                            acc = w9[:, kh, kw] if acc is None else acc + w9[:, kh, kw]
+                    out[2 * py + px, :, dy, dx] = acc
+    return out.view(4, cout, 4 * cin).contiguous()
+
+
+def conv2d_tc_up2_supported(B, H, W, Cin, Cout):
+    return bool(_lib.load().sgam_conv2d_tc_up2_supported(B, H, W, Cin, Cout))
+
+
+def conv2d_tc_up2(x, w, bias, nsplit=3, gn_stats=True):
+    """Upsample (nearest x2 + 3x3 conv) in sub-pixel form on tcgen05.  x = (hi, lo) bf16 [B,H,W,Cin] at LOW resolution;
+    w = (hi, lo) bf16 [4, Cout, 4*Cin] from `subpixel_weights`; returns fp32 y [B,2H,2W,Cout] (+ fused GroupNorm statistics)."""
+    lib = _lib.load()
+    x_hi, x_lo = x
+    w_hi, w_lo = w
+    for n, t in (("x_hi", x_hi), ("x_lo", x_lo), ("w_hi", w_hi), ("w_lo", w_lo)):
+        _chk(t, torch.bfloat16, n)
+    B, H, W, Cin = x_hi.shape
+    Cout = w_hi.shape[1]
+    if tuple(w_hi.shape) != (4, Cout, 4 * Cin):
+        raise RuntimeError(f"conv2d_tc_up2: weight {tuple(w_hi.shape)} does not match Cin={Cin}")
+    y = torch.empty(B, 2 * H, 2 * W, Cout, device=x_hi.device)
+    partial = None
+    if gn_stats and Cout % 128 == 0 and Cout <= 512:
+        partial = torch.empty(lib.sgam_tc_gn_partial_floats(B, 2 * H, 2 * W), device=x_hi.device)
+    _lib.check(lib.sgam_conv2d_tc_up2(x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), _ptr(bias), y.data_ptr(),
+                                      B, H, W, Cin, Cout, nsplit, _ptr(partial), _stream()), "sgam_conv2d_tc_up2")
+    if partial is not None:
+        y.gn_partial = partial
+    return y

@@ -34,6 +34,7 @@ class VQGANEngine:
         self.mode, self.nsplit = mode, nsplit
         import os
         self.fused_head = os.environ.get("SGAM_FUSED_HEAD", "1") != "0"
+        self.subpixel = os.environ.get("SGAM_SUBPIXEL", "1") != "0"
         self.p = {}
         self.wsplit = {}
         self.load_state_dict(state_dict)
@@ -64,6 +65,10 @@ class VQGANEngine:
             for k, v in p.items():
                 if k.endswith(".weight") and v.dim() == 2 and k != "quantize.embedding.weight" and v.shape[1] % 64 == 0:
                     self.wsplit[k[:-len(".weight")]] = ops.split_weight(v, pad_rows_to=32)
+            # Upsample convs (nearest x2 + 3x3) also in sub-pixel form: four 2x2 parity filters on the low-resolution tensor
+            for k, v in p.items():
+                if k.endswith(".upsample.conv.weight") and v.dim() == 2 and v.shape[1] % (9 * 64) == 0:
+                    self.wsplit[k[:-len(".weight")] + ".subpixel"] = ops.split_weight(ops.subpixel_weights(v, v.shape[1] // 9))
             # encoder.conv_in has Cin = 4: zero-pad each tap's channels to 64 so it runs on the tensor cores as well
             w = p["encoder.conv_in.weight"]
             cin = self.dd["in_channels"]
@@ -193,7 +198,13 @@ class VQGANEngine:
                 if self.has(f"decoder.up.{l}.attn.{b}.norm"):
                     h = self.attn_block(f"decoder.up.{l}.attn.{b}", h)
             if l != 0:
-                h = self.conv_from_f32(f"decoder.up.{l}.upsample.conv", h, 3, upsample=1)
+                name = f"decoder.up.{l}.upsample.conv"
+                Bh, Hh, Wh, Ch = h.shape
+                if self.subpixel and f"{name}.subpixel" in self.wsplit and \
+                        ops.conv2d_tc_up2_supported(Bh, Hh, Wh, Ch, self.p[f"{name}.weight"].shape[0]):
+                    h = ops.conv2d_tc_up2(ops.split_bf16(h), self.wsplit[f"{name}.subpixel"], self.p[f"{name}.bias"], nsplit=self.nsplit)
+                else:
+                    h = self.conv_from_f32(name, h, 3, upsample=1)
         w_out = self.p["decoder.conv_out.weight"]
         if self.mode == "tc" and self.fused_head and getattr(h, "gn_partial", None) is not None and h.shape[-1] == 128 \
                 and w_out.shape == (4, 9 * 128):

@@ -308,3 +308,31 @@ def test_fused_groupnorm_swish_head_conv(ops, shape):
     w_t = w.permute(2, 3, 1, 0).reshape(9, 128, 4).contiguous().cuda()
     y = ops.gn_head_conv(xn, ga.cuda(), be.cuda(), w_t, bias.cuda())
     assert tuple(y.shape) == (B, 4, H, W) and rel(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(3, 128, 128, 128, 128), (5, 64, 64, 256, 256), (10, 64, 64, 128, 256)])
+def test_subpixel_upsample_conv(ops, case):
+    """Upsample = nearest x2 + conv3x3 (diffusionmodules/model.py:49-52) as four 2x2 parity convolutions of the LOW-resolution
+    tensor (swapped-operand kernel for 128 output channels, pair kernel for 256) vs interpolate + conv2d in fp64, plus the
+    GroupNorm statistics the four launches leave in one buffer."""
+    B, H, W, Cin, Cout = case
+    assert ops.conv2d_tc_up2_supported(B, H, W, Cin, Cout)
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    ga, be = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    ref = F.conv2d(F.interpolate(x.cuda().double(), scale_factor=2.0, mode="nearest"), w.cuda().double(), bias.cuda().double(), padding=1)
+    xs = ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda())
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda()
+    ws = ops.split_weight(ops.subpixel_weights(wp, Cin))
+    y = ops.conv2d_tc_up2(xs, ws, bias.cuda())
+    assert tuple(y.shape) == (B, 2 * H, 2 * W, Cout) and rel(y.permute(0, 3, 1, 2), ref) < 5e-5
+    # same result as the 3x3 form on the up-sampled operand (different rounding of the pre-summed taps only)
+    y3 = ops.conv2d_tc(ops.split_bf16(x.permute(0, 2, 3, 1).contiguous().cuda(), upsample=1), ops.split_weight(wp, pad_rows_to=32), bias.cuda(), ksize=3)
+    assert rel(y, y3) < 2e-5
+    gn = F.group_norm(ref, 32, ga.cuda().double(), be.cuda().double(), eps=1e-6)
+    gn = gn * torch.sigmoid(gn)
+    assert hasattr(y, "gn_partial")
+    hi, lo = ops.groupnorm_split(y, ga.cuda(), be.cuda(), True)
+    assert rel((hi.float() + lo.float()).permute(0, 3, 1, 2), gn) < 5e-5
