@@ -294,6 +294,11 @@ class StepHarness:
         def gemm_flops(a, kw, y):
             return 2.0 * first(y).numel() * a[0][0].shape[-1]
 
+        def up2_flops(a, kw, y):                   # the reference's op: 3x3 conv on the 2x up-sampled tensor (the sub-pixel form issues 4/9 of it)
+            w = a[1][0]
+            cout, cin = w.shape[1], w.shape[2] // 4
+            return 2.0 * (first(y).numel() // cout) * cout * 9 * cin
+
         def attn_flops(a, kw, y):                  # QK^T + PV
             q = a[0][0]
             Bq, T, C = q.shape
@@ -311,9 +316,8 @@ class StepHarness:
                 return y
             return wrapper
 
-        patched = {"conv2d_tc": (ops.conv2d_tc, conv_flops), "gemm_nt_tc": (ops.gemm_nt_tc, gemm_flops)}
-        if hasattr(ops, "attention_tc"):
-            patched["attention_tc"] = (ops.attention_tc, attn_flops)
+        patched = {"conv2d_tc": (ops.conv2d_tc, conv_flops), "gemm_nt_tc": (ops.gemm_nt_tc, gemm_flops),
+                   "attention_tc": (ops.attention_tc, attn_flops), "conv2d_tc_up2": (ops.conv2d_tc_up2, up2_flops)}
         for name, (fn, fl) in patched.items():
             setattr(ops, name, timed(fn, fl))
         try:
@@ -326,6 +330,7 @@ class StepHarness:
                 setattr(ops, name, fn)
         ms = sum(ev[0].elapsed_time(ev[1]) for ev in events)
         flops = sum(ev[2] for ev in events)
+        issued = sum(ev[2] * (4.0 / 9.0 if ev[3] == "conv2d_tc_up2" else 1.0) for ev in events)     # MMA work actually issued (x nsplit)
         if dump:
             with open(dump, "w") as f:
                 f.write("op\tshape(A|B)\tkw\tGFLOP\tms\tTFLOP/s(algorithmic)\n")
@@ -334,6 +339,12 @@ class StepHarness:
                     f.write(f"{ev[3]}\t{ev[4]}\t{ev[5]}\t{ev[2] / 1e9:.2f}\t{t:.4f}\t{ev[2] / t / 1e9:.1f}\n")
         tflops = flops / (ms * 1e-3) / 1e12
         nsplit = eng.nsplit if eng.mode == "tc" else 1
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.resident()
+        e1.record()
+        torch.cuda.synchronize()
+        eager_ms = e0.elapsed_time(e1)              # the per-call events were taken on EAGER launches: compare like with like
         by_op = {}
         for ev in events:
             d = by_op.setdefault(ev[3], [0, 0.0, 0.0])
@@ -342,12 +353,16 @@ class StepHarness:
                 "bound": "tensor", "achieved": tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tflops / peaks["tflops"],
                 "algorithmic_bytes_per_launch": sum(ev[6] for ev in events) / max(1, len(events)),
                 "peak_source": peaks["source"] + ", sustained bf16",
-                "launches_per_step": len(events), "ms_per_step": ms, "share_of_step": ms / step_ms,
-                "flops_per_step": flops, "mma_issue_tflops": tflops * nsplit, "frac_mma_issue": tflops * nsplit / peaks["tflops"],
+                "launches_per_step": len(events), "ms_per_step": ms, "share_of_step": ms / max(eager_ms, step_ms),
+                "eager_step_ms": eager_ms,
+                "flops_per_step": flops, "mma_issue_tflops": issued * nsplit / (ms * 1e-3) / 1e12,
+                "frac_mma_issue": issued * nsplit / (ms * 1e-3) / 1e12 / peaks["tflops"],
                 "by_op": {k: {"calls": v[0], "ms": v[1], "tflops": v[2] / (v[1] * 1e-3) / 1e12} for k, v in by_op.items()},
-                "note": "achieved counts ALGORITHMIC flops (2*M*N*K of the fp32 conv / attention products, the zero-padded "
-                        "stem at its real K); every product is issued as 3 bf16 MMAs (hi*hi + hi*lo + lo*hi) to stay within "
-                        "1e-3 of the fp32 reference, so the tensor pipe runs at mma_issue_tflops"}
+                "note": "achieved counts ALGORITHMIC flops of the reference's operators (2*M*N*K of the fp32 conv / attention "
+                        "products, the zero-padded stem at its real K, the Upsample convs as 3x3 on the up-sampled tensor although "
+                        "the sub-pixel form issues 4/9 of that); every product is issued as 3 bf16 MMAs (hi*hi + hi*lo + lo*hi) "
+                        "to stay within 1e-3 of the fp32 reference, so the tensor pipe runs at mma_issue_tflops; the 4-channel "
+                        "decoder head runs on the FP32 pipes (gn_head_conv) and is not part of this figure"}
 
 
 def measure(h, steps, warmup, world):
