@@ -225,6 +225,13 @@ long long sgam_tc_gn_partial_floats(int B, int Ho, int Wo);
 int sgam_groupnorm_split_fused(const float *x, const float *gamma, const float *beta, void *hi, void *lo,
                                float *gn_partial, int B, int Ho, int Wo, int C, int swish, void *stream);
 
+/* Encoder entry: the stem (cat(x, mask) -> 1x1 conv 5 -> 4, model.py:106-113) + encoder.conv_in (3x3, 4 -> 128,
+ * diffusionmodules/model.py:370) + the GroupNorm partial sums of the result in one exact-fp32 kernel (36 real taps: FP32-pipe
+ * work, not a K = 576 zero-padded GEMM).  x [B,4,H,W] NCHW, mask [B,H,W] u8 or NULL, w1 [4,5], b1 [4], w3 [128, 36]
+ * K-major (kh, kw, ci), b3 [128]; y fp32 NHWC [B,H,W,128]; gn_partial: sgam_tc_gn_partial_floats(B,H,W) floats or NULL. */
+int sgam_stem_conv_in(const float *x, const uint8_t *mask, const float *w1, const float *b1, const float *w3, const float *b3,
+                      float *y, float *gn_partial, int B, int H, int W, int Cout, void *stream);
+
 /* Decoder head: decoder.norm_out (GroupNorm(32,128), eps 1e-6) + swish + decoder.conv_out (3x3, 128 -> 4, NCHW output;
  * diffusionmodules/model.py:534-538) in one exact-fp32 kernel: the normalised halo tile is staged in shared memory once,
  * the channel reduction runs on the FP32 pipes (a 4-column GEMM tile would waste 97 % of the tensor pipe and re-read the

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sgam_gemm_nt_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p]),
     "sgam_conv2d_tc_up2_supported": (c_i, [c_i, c_i, c_i, c_i, c_i]),
     "sgam_conv2d_tc_up2": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "sgam_stem_conv_in": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sgam_gn_head_conv": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sgam_attention_tc_supported": (c_i, [c_i, c_i, c_i]),
     "sgam_attention_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p]),

@@ -403,46 +403,6 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
         p.stats = gn_partial; p.cpg = Cout / 32;
         return launch_tc2(BN2, a_hi, a_lo, b_hi, b_lo, p, B, Ho, Wo, Npad, (cudaStream_t)stream);
     }
-    // pair kernel on a partial grid: unsplit when its 256-row x 256-column tiles already cover most SM pairs, with a split K
-    // loop (raw partial tiles + the deterministic reduce kernel, which also takes the GroupNorm statistics) otherwise
-    const bool plain_out = y && !y_hi && !out_nchw && Npad == Cout;
-    const int ks2 = (plain_out && tc_use_2cta()) ? tc2_splitk_plan(B, Ho, Wo, Npad, ksize * ksize * (Cin / 64), &BN2) : 0;
-    if (ks2 == 1 || (ks2 > 1 && splitk_ws && !gn_partial)) {
-        CUtensorMap a_hi, a_lo, b_hi, b_lo;
-        const int bw = Wo >= 256 ? 128 : Wo, bh = Wo >= 256 ? 1 : 128 / Wo;
-        const long long adims[4] = {Cin, W, H, B};
-        const int abox[4] = {64, bw * stride, bh * stride, 1};
-        const int astr[4] = {1, stride, stride, 1};
-        const long long bdims[3] = {(long long)ksize * ksize * Cin, Npad, 1};
-        const int bbox[3] = {64, BN2 / 2, 1};
-        int rc;
-        if ((rc = make_map(&a_hi, x_hi, 4, adims, abox, astr)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox, astr)) ||
-            (rc = make_map(&b_hi, w_hi, 3, bdims, bbox)) || (rc = make_map(&b_lo, w_lo, 3, bdims, bbox)))
-            return rc;
-        TcParams p{};
-        p.Ho = Ho; p.Wo = Wo; p.taps = ksize * ksize; p.ks = ksize; p.pad = (stride == 1) ? ksize / 2 : 0; p.stride = stride;
-        p.kblocks_per_tap = Cin / 64; p.N = Cout; p.n_valid = Cout; p.nsplit = nsplit; p.a_batched = 1;
-        p.d_batch_stride = (long long)Ho * Wo * Cout; p.alpha = 1.0f; p.D = y;
-        const int num_kb = p.taps * p.kblocks_per_tap;
-        if (ks2 == 1) {
-            p.bias_n = bias; p.R = residual; p.stats = gn_partial; p.cpg = Cout / 32;
-            return launch_tc2(BN2, a_hi, a_lo, b_hi, b_lo, p, B, Ho, Wo, Npad, (cudaStream_t)stream);
-        }
-        p.ksplit = ks2; p.kb_per_split = cdiv(num_kb, ks2);
-        p.splitk_ws = splitk_ws; p.split_stride = (long long)B * Ho * Wo * Cout;
-        if ((rc = launch_tc2(BN2, a_hi, a_lo, b_hi, b_lo, p, B, Ho, Wo, Npad, (cudaStream_t)stream))) return rc;
-        const long long total_q = p.split_stride / 4;
-        if (splitk_gn_partial && Cout % 128 == 0 && Cout <= 1024) {
-            const long long HW = (long long)Ho * Wo;
-            const int S = sgam_gn_splits(HW);
-            SGAM_PDL_LAUNCH(SGAM_PDL_MISC, splitk_reduce_stats_kernel, dim3(S, B), 256, 0, (cudaStream_t)stream, splitk_ws, p.split_stride, p.ksplit, bias,
-                            residual, y, splitk_gn_partial, HW, Cout, S);
-            return SGAM_OK;
-        }
-        const unsigned blocks = (unsigned)min((long long)148 * 4, (total_q + 255) / 256);
-        SGAM_PDL_LAUNCH(SGAM_PDL_MISC, splitk_reduce_kernel, blocks, 256, 0, (cudaStream_t)stream, splitk_ws, p.split_stride, p.ksplit, bias, residual, y, total_q, Cout / 4);
-        return SGAM_OK;
-    }
     TilePlan t = plan_tiles(B, Ho, Wo, Npad, (splitk_ws && !gn_partial) ? ksize * ksize * (Cin / 64) : 0);
     if (stride == 2 && t.MT == 2) { t.MT = 1; t.BW = Wo >= 128 ? 128 : Wo; t.BH = 128 / t.BW; }   // TMA box extent <= 256 elements
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -547,16 +507,6 @@ extern "C" long long sgam_conv2d_tc_splitk_floats(int B, int H, int W, int Cin, 
     if (stride != 1 && stride != 2) return 0;
     const int Ho = H / stride, Wo = W / stride;
     if (Ho <= 0 || Wo <= 0 || !sgam_tc_supported_conv(Ho, Wo, Cin, Cout, ksize, stride) || Cout % 32) return 0;
-    {   // the same decisions, in the same order, as sgam_conv2d_tc: swap kernel, full-grid pair kernel (neither splits K) ...
-        int bn2 = 0;
-        if (swap_applicable(B, Ho, Wo, Cin, Cout, stride, true)) return 0;
-        if (tc_use_2cta() && tc2_applicable(B, Ho, Wo, Cout, stride, 0, Cout, &bn2)) return 0;
-        // ... then the pair kernel with a split K loop
-        const int num_kb = ksize * ksize * (Cin / 64);
-        const int ks2 = tc_use_2cta() ? tc2_splitk_plan(B, Ho, Wo, Cout, num_kb, &bn2) : 0;
-        if (ks2 > 1) return (long long)ks2 * B * Ho * Wo * Cout;
-        if (ks2 == 1) return 0;
-    }
     TilePlan t = plan_tiles(B, Ho, Wo, Cout, ksize * ksize * (Cin / 64));
     if (stride == 2 && t.MT == 2) { t.MT = 1; t.BW = Wo >= 128 ? 128 : Wo; t.BH = 128 / t.BW; }
     const long long tiles = (long long)cdiv(Wo, t.BW) * cdiv(Ho, t.BH) * B * cdiv(Cout, t.BN);

@@ -55,7 +55,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int num_kb = p.taps * p.kblocks_per_tap;
-    const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit;   // pair tiles x column tiles x k-splits (split index fastest)
+    const int total_tiles = p.tiles_m * p.tiles_n;              // pair tiles x column tiles
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -79,15 +79,13 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             const uint32_t tx_bytes = (p.nsplit == 3) ? STAGE_BYTES : (A_PLANE + B_PLANE);
             int kbg = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-                const int ksp = tile % p.ksplit, mn = tile / p.ksplit;
-                const int kb0 = ksp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-                const int n0 = (mn % p.tiles_n) * BN + (int)rank * (BN / 2);
-                int t = mn / p.tiles_n;
+                const int n0 = (tile % p.tiles_n) * BN + (int)rank * (BN / 2);
+                int t = tile / p.tiles_n;
                 const int tx = t % g.tiles_x2; t /= g.tiles_x2;
                 const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
                 const int ox0 = tx * g.BW2 + (int)rank * g.dx, oy0 = ty * g.BH2 + (int)rank * g.dy;
                 const int ab = p.a_batched ? b : 0, bb = p.b_batched ? b : 0;
-                for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
+                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
                     const int s = kbg % STAGES, it = kbg / STAGES;
                     mbar_wait(&empty_bar[s], (it & 1) ^ 1);
                     uint8_t *st = smem + (size_t)s * STAGE_BYTES;
@@ -112,12 +110,10 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             int kbg = 0, li = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++li) {
                 const int acc = li & 1;
-                const int ksp = tile % p.ksplit;
-                const int kb0 = ksp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 mbar_wait(&tmem_empty_bar[acc], ((li >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
+                for (int kb = 0; kb < num_kb; ++kb, ++kbg) {
                     const int s = kbg % STAGES, it = kbg / STAGES;
                     mbar_wait(&full_bar[s], it & 1);
                     tc_fence_after();
@@ -127,7 +123,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t off = (uint64_t)(k * 2);
-                        umma2_bf16(tmem_d, a_hi + off, b_hi + off, idesc, (kb != kb0 || k) ? 1u : 0u);
+                        umma2_bf16(tmem_d, a_hi + off, b_hi + off, idesc, (kb | k) ? 1u : 0u);
                         if (p.nsplit == 3) {
                             umma2_bf16(tmem_d, a_hi + off, b_lo + off, idesc, 1u);
                             umma2_bf16(tmem_d, a_lo + off, b_hi + off, idesc, 1u);
@@ -144,9 +140,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
         int li = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++li) {
             const int acc = li & 1;
-            const int ksp = tile % p.ksplit, mn = tile / p.ksplit;
-            const int n_tile = mn % p.tiles_n, n0 = n_tile * BN;
-            int t = mn / p.tiles_n;
+            const int n_tile = tile % p.tiles_n, n0 = n_tile * BN;
+            int t = tile / p.tiles_n;
             const int m2 = t % (g.tiles_x2 * g.tiles_y2);
             const int tx = t % g.tiles_x2; t /= g.tiles_x2;
             const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
@@ -156,7 +151,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const long long per_img = p.stat_tiles ? p.stat_tiles : 2LL * g.tiles_x2 * g.tiles_y2;
             const long long slot = (long long)b * per_img + p.stat_tile0 + (long long)m2 * 2 + rank;
-            epilogue_rows<BN>(p, tmem_acc, q * 32 + lane, b, oy0, ox0, n0, n_tile, ksp, slot, stat_s, epi_stage, q, lane);
+            epilogue_rows<BN>(p, tmem_acc, q * 32 + lane, b, oy0, ox0, n0, n_tile, 0, slot, stat_s, epi_stage, q, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(map_to_cta(&tmem_empty_bar[acc], 0));
@@ -180,7 +175,7 @@ int launch2_cfg(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensor
         SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
-    const int total = p.tiles_m * p.tiles_n * p.ksplit, max_clusters = sm_count_cached() / 2;
+    const int total = p.tiles_m * p.tiles_n, max_clusters = sm_count_cached() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
     SGAM_PDL_LAUNCH(SGAM_PDL_GEMM2, (tc_gemm2_kernel<BN, STAGES>), 2 * clusters, TC_THREADS, Cfg::SMEM, s, a_hi, a_lo, b_hi, b_lo, p, g);
     return SGAM_OK;
@@ -205,28 +200,6 @@ bool tc2_applicable(int B, int Ho, int Wo, int N, int stride, int out_nchw, int 
     return true;
 }
 
-// Pair kernel with a split K loop for long-K layers whose pair-tile grid is a fraction of the machine (512-channel convs
-// at 16x16, 256-channel ones at 32x32, at several trajectories): the 1-CTA kernel fills the SMs with 64/128-wide tiles
-// that each pull a full-K slab of activations AND weights through L2 (the measured limiter); a
-// 256-row pair tile with 256 columns moves half the bytes per MMA and each CTA stages only half of the weight tile.
-// Returns the split count (0 = do not use this path) and the column-tile width.
-int tc2_splitk_plan(int B, int Ho, int Wo, int N, int num_kb, int *BN_out) {
-    if (N % 128 || num_kb < 16) return 0;
-    const bool exact = (Wo >= 256) ? (Wo % 256 == 0) : (Wo >= 2 && 256 % Wo == 0 && (Wo & (Wo - 1)) == 0 && Ho % (256 / Wo) == 0);
-    if (!exact) return 0;
-    const long long pair_tiles = (long long)B * ((long long)Ho * Wo / 256);
-    const int BN = (N % 256 == 0) ? 256 : 128;
-    const long long clusters0 = pair_tiles * (N / BN);
-    const int max_clusters = sm_count_cached() / 2;
-    if (clusters0 < 8 || clusters0 >= max_clusters) return 0;             // tiny grids: 1-CTA split-K; full grids: plain pair kernel
-    int ks = (int)(max_clusters / clusters0);
-    if (ks > num_kb / 4) ks = num_kb / 4;
-    if (ks < 1) ks = 1;
-    const int per = (num_kb + ks - 1) / ks;
-    *BN_out = BN;
-    return (num_kb + per - 1) / per;
-}
-
 // p carries everything except the tiling; a/b maps must have been built with box rows 128 (A) and BN/2 (B).
 int launch_tc2(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, TcParams p,
                int B, int Ho, int Wo, int N, cudaStream_t s) {
@@ -237,7 +210,7 @@ int launch_tc2(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const C
     p.tiles_x = g.tiles_x2; p.tiles_y = g.tiles_y2;
     p.tiles_m = g.tiles_x2 * g.tiles_y2 * B;
     p.tiles_n = N / BN;
-    if (p.ksplit <= 1) { p.ksplit = 1; p.kb_per_split = p.taps * p.kblocks_per_tap; }
+    p.ksplit = 1; p.kb_per_split = p.taps * p.kblocks_per_tap;
     if (BN == 256) return launch2_cfg<256, 3>(a_hi, a_lo, b_hi, b_lo, p, g, s);
     return launch2_cfg<128, 4>(a_hi, a_lo, b_hi, b_lo, p, g, s);
 }

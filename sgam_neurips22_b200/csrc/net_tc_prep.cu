@@ -242,17 +242,32 @@ gn_head_conv_kernel(const float *__restrict__ x, const float *__restrict__ meanr
         const float mean = meanrstd[(b * 32 + lane) * 2], rstd = meanrstd[(b * 32 + lane) * 2 + 1];   // group = channel quad (128 / 32 = 4)
         const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma) + lane), be = __ldg(reinterpret_cast<const float4 *>(beta) + lane);
         const float4 *src = reinterpret_cast<const float4 *>(x) + (size_t)b * H * W * 32;
-        for (int pix = warp; pix < (HD_TH + 2) * (HD_TW + 2); pix += 4) {
-            const int gy = y0 - 1 + pix / (HD_TW + 2), gx = x0 - 1 + pix % (HD_TW + 2);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                v = __ldg(src + ((size_t)gy * W + gx) * 32 + lane);
-                v.x = (v.x - mean) * rstd * ga.x + be.x; v.y = (v.y - mean) * rstd * ga.y + be.y;
-                v.z = (v.z - mean) * rstd * ga.z + be.z; v.w = (v.w - mean) * rstd * ga.w + be.w;
-                v.x = __fdividef(v.x, 1.0f + __expf(-v.x)); v.y = __fdividef(v.y, 1.0f + __expf(-v.y));
-                v.z = __fdividef(v.z, 1.0f + __expf(-v.z)); v.w = __fdividef(v.w, 1.0f + __expf(-v.w));
+        // 180 halo pixels, 45 per warp, in batches of 9 whose loads are all in flight before the first is used (a loop of
+        // load -> transform -> store exposed one full DRAM latency per pixel: 460 us for the layer, ncu pass E)
+        constexpr int PER_WARP = (HD_TH + 2) * (HD_TW + 2) / 4, BATCH = 9;
+        static_assert(PER_WARP * 4 == (HD_TH + 2) * (HD_TW + 2) && PER_WARP % BATCH == 0, "halo tile must split evenly");
+#pragma unroll 1
+        for (int b0 = 0; b0 < PER_WARP; b0 += BATCH) {
+            float4 v[BATCH];
+            bool ok[BATCH];
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int pix = warp + 4 * (b0 + i);
+                const int gy = y0 - 1 + pix / (HD_TW + 2), gx = x0 - 1 + pix % (HD_TW + 2);
+                ok[i] = gy >= 0 && gy < H && gx >= 0 && gx < W;
+                v[i] = ok[i] ? __ldg(src + ((size_t)gy * W + gx) * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            hs[pix * 32 + lane] = v;
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                float4 t = v[i];
+                if (ok[i]) {
+                    t.x = (t.x - mean) * rstd * ga.x + be.x; t.y = (t.y - mean) * rstd * ga.y + be.y;
+                    t.z = (t.z - mean) * rstd * ga.z + be.z; t.w = (t.w - mean) * rstd * ga.w + be.w;
+                    t.x = __fdividef(t.x, 1.0f + __expf(-t.x)); t.y = __fdividef(t.y, 1.0f + __expf(-t.y));
+                    t.z = __fdividef(t.z, 1.0f + __expf(-t.z)); t.w = __fdividef(t.w, 1.0f + __expf(-t.w));
+                }
+                hs[(warp + 4 * (b0 + i)) * 32 + lane] = t;
+            }
         }
     }
     // ---- this lane's filter taps: wr[tap][channel of the quad] = the 4 output channels
@@ -321,6 +336,94 @@ gn_head_conv_kernel(const float *__restrict__ x, const float *__restrict__ meanr
                 const float bv = o == 0 ? bo.x : (o == 1 ? bo.y : (o == 2 ? bo.z : bo.w));
                 y[((size_t)b * 4 + o) * plane + (size_t)gy * W + gx] = r1 + bv;
             }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ encoder stem
+// VQModel.encode's stem (cat(x, mask) -> 1x1 conv 5 -> 4, model.py:106-113) + encoder.conv_in (3x3, 4 -> 128,
+// diffusionmodules/model.py:370) + the GroupNorm partial sums of the result, as ONE exact-fp32 kernel.  Round 1 ran
+// conv_in on the tensor cores by zero-padding its 4 input channels to 64 (K = 576 for 36 real taps: 94 % of the MMA work
+// and of the 537 MB padded operand were zeros; 59 us + 169 us at 8 trajectories).  The layer is 4608 FMAs per pixel --
+// FP32-pipe work: a CTA owns one 128-pixel block of the statistics layout (BW x BH pixels), stages the 4-channel stem
+// values of its halo in shared memory (zero outside the image: the conv pads the STEM OUTPUT), thread c owns output channel
+// c with its 36 taps in registers and walks the block in segments of four pixels (the 3 x 6 window is read once with
+// broadcast 16-byte loads), writes 512-byte rows, and the per-channel sums are folded to the 32 groups with two shuffles.
+__global__ void __launch_bounds__(128)
+stem_conv_in_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask, const float *__restrict__ w1, const float *__restrict__ b1,
+                    const float *__restrict__ w3 /* [128][9*4] */, const float *__restrict__ b3, float *__restrict__ y,
+                    float *__restrict__ stats, int H, int W, int BW, int BH, int tiles_x, int tiles) {
+    SGAM_PDL_PROLOGUE();
+    extern __shared__ float4 st[];                                  // [(BH+2)][(BW+2)] stem values (4 channels)
+    const int b = blockIdx.y, tile = blockIdx.x, ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int y0 = ty * BH, x0 = tx * BW, c = threadIdx.x, SW = BW + 2;
+    const size_t HW = (size_t)H * W;
+    for (int p = threadIdx.x; p < (BH + 2) * SW; p += 128) {
+        const int gy = y0 - 1 + p / SW, gx = x0 - 1 + p % SW;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const size_t pix = (size_t)gy * W + gx;
+            float in[5];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) in[k] = __ldg(x + ((size_t)b * 4 + k) * HW + pix);
+            in[4] = mask ? (mask[(size_t)b * HW + pix] ? 1.0f : 0.0f) : 0.0f;
+            float r[4];
+#pragma unroll
+            for (int co = 0; co < 4; ++co) {
+                float a = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) a = fmaf(in[k], __ldg(w1 + co * 5 + k), a);
+                r[co] = a + __ldg(b1 + co);
+            }
+            o = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        st[p] = o;
+    }
+    float4 wr[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t] = __ldg(reinterpret_cast<const float4 *>(w3) + c * 9 + t);
+    const float bias = __ldg(b3 + c);
+    __syncthreads();
+    float s_acc = 0.0f, q_acc = 0.0f;
+    for (int ly = 0; ly < BH; ++ly) {
+        const int gy = y0 + ly;
+        if (gy >= H) break;
+#pragma unroll 1
+        for (int lx = 0; lx < BW; lx += 4) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                float4 v[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v[j] = st[(ly + kh) * SW + lx + j];
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float4 wt = wr[kh * 3 + kw];
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        acc[px] = fmaf(v[px + kw].x, wt.x, acc[px]); acc[px] = fmaf(v[px + kw].y, wt.y, acc[px]);
+                        acc[px] = fmaf(v[px + kw].z, wt.z, acc[px]); acc[px] = fmaf(v[px + kw].w, wt.w, acc[px]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                const int gx = x0 + lx + px;
+                if (gx < W) {
+                    const float o = acc[px] + bias;
+                    y[(((size_t)b * H + gy) * W + gx) * 128 + c] = o;
+                    s_acc += o; q_acc = fmaf(o, o, q_acc);
+                }
+            }
+        }
+    }
+    if (stats) {                                                    // channels 4g .. 4g+3 = group g: lanes 4g .. 4g+3
+        s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 1); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 1);
+        s_acc += __shfl_xor_sync(0xffffffffu, s_acc, 2); q_acc += __shfl_xor_sync(0xffffffffu, q_acc, 2);
+        if ((c & 3) == 0) {
+            float *dst = stats + (((size_t)b * tiles + tile) * 32 + (c >> 2)) * 2;
+            dst[0] = s_acc; dst[1] = q_acc;
         }
     }
 }
@@ -424,5 +527,21 @@ extern "C" int sgam_gn_head_conv(const float *x, const float *gamma, const float
         configured = true;
     }
     SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_head_conv_kernel, dim3(cdiv(W, HD_TW), cdiv(H, HD_TH), B), 128, HD_SMEM, s, x, meanrstd, gamma, beta, w_t, bias, y, H, W);
+    return SGAM_OK;
+}
+
+// Stem + encoder.conv_in + GroupNorm partial sums in one fp32 kernel (see stem_conv_in_kernel).  x [B,4,H,W] NCHW, mask
+// [B,H,W] u8 or NULL, w1 [4,5] / b1 [4] (the 1x1 stem), w3 [128, 9*4] K-major (kh, kw, ci) / b3 [128]; y fp32 NHWC
+// [B,H,W,128]; gn_partial (sgam_tc_gn_partial_floats(B,H,W) floats) or NULL.
+extern "C" int sgam_stem_conv_in(const float *x, const uint8_t *mask, const float *w1, const float *b1, const float *w3,
+                                 const float *b3, float *y, float *gn_partial, int B, int H, int W, int Cout, void *stream) {
+    SGAM_REQUIRE(x && w1 && b1 && w3 && b3 && y, "stem_conv_in: null pointer");
+    SGAM_REQUIRE(B > 0 && H > 0 && W >= 4 && Cout == 128, "stem_conv_in: needs 128 output channels and W >= 4 (W=%d Cout=%d)", W, Cout);
+    SGAM_REQUIRE(W % 128 == 0 || ((W & (W - 1)) == 0 && W <= 128), "stem_conv_in: W must be a power of two <= 128 or a multiple of 128");
+    const int BW = W >= 128 ? 128 : W, BH = 128 / BW;
+    const int tiles_x = cdiv(W, BW), tiles = tiles_x * cdiv(H, BH);
+    const size_t smem = (size_t)(BH + 2) * (BW + 2) * sizeof(float4);
+    SGAM_PDL_LAUNCH(SGAM_PDL_MISC, stem_conv_in_kernel, dim3(tiles, B), 128, smem, (cudaStream_t)stream, x, mask, w1, b1, w3, b3, y, gn_partial, H, W,
+                    BW, BH, tiles_x, tiles);
     return SGAM_OK;
 }

@@ -55,7 +55,6 @@ inline int sm_count_cached() {
 // 2-CTA kernel (net_tc2.cu)
 struct TcParams;
 bool tc2_applicable(int B, int Ho, int Wo, int N, int stride, int out_nchw, int n_valid, int *BN_out);
-int tc2_splitk_plan(int B, int Ho, int Wo, int N, int num_kb, int *BN_out);
 int launch_tc2(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, TcParams p,
                int B, int Ho, int Wo, int N, cudaStream_t s);
 // swapped-operand kernel for 128-channel convolutions (net_tc3.cu)

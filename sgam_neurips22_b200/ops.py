@@ -556,3 +556,21 @@ def conv2d_tc_up2(x, w, bias, nsplit=3, gn_stats=True):
     if partial is not None:
         y.gn_partial = partial
     return y
+
+
+def stem_conv_in(x, mask, w1, b1, w3, b3, gn_stats=True):
+    """Stem (model.py:106-113) + encoder.conv_in (3x3, 4 -> 128) + GroupNorm partial sums in one fp32 kernel.
+    x [B,4,H,W] NCHW, mask [B,H,W] uint8 or None -> fp32 NHWC [B,H,W,128] (with `.gn_partial`)."""
+    lib = _lib.load()
+    _chk(x, name="x"), _chk(w1, name="w1"), _chk(b1, name="b1"), _chk(w3, name="w3"), _chk(b3, name="b3")
+    if mask is not None:
+        _chk(mask, torch.uint8, "mask")
+    B, _, H, W = x.shape
+    Cout = w3.shape[0]
+    y = torch.empty(B, H, W, Cout, device=x.device)
+    partial = torch.empty(lib.sgam_tc_gn_partial_floats(B, H, W), device=x.device) if gn_stats else None
+    _lib.check(lib.sgam_stem_conv_in(x.data_ptr(), _ptr(mask), w1.data_ptr(), b1.data_ptr(), w3.data_ptr(), b3.data_ptr(), y.data_ptr(),
+                                     _ptr(partial), B, H, W, Cout, _stream()), "sgam_stem_conv_in")
+    if partial is not None:
+        y.gn_partial = partial
+    return y

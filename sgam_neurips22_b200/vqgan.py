@@ -35,6 +35,7 @@ class VQGANEngine:
         import os
         self.fused_head = os.environ.get("SGAM_FUSED_HEAD", "1") != "0"
         self.subpixel = os.environ.get("SGAM_SUBPIXEL", "1") != "0"
+        self.fused_stem = os.environ.get("SGAM_FUSED_STEM", "1") != "0"
         self.p = {}
         self.wsplit = {}
         self.load_state_dict(state_dict)
@@ -224,7 +225,11 @@ class VQGANEngine:
         if mask is not None:
             mask = mask.reshape(mask.shape[0], *mask.shape[-2:])
         B, _, H, W = x.shape
-        if self.mode == "tc" and "encoder.conv_in.padded" in self.wsplit and \
+        w3 = self.p["encoder.conv_in.weight"]
+        if self.mode == "tc" and self.fused_stem and w3.shape == (128, 36) and W >= 4 and ops.tc_supported_conv(H, W, 64, 128, 3, 1):
+            # stem + conv_in + GroupNorm statistics as one fp32 kernel (36 real taps are FP32-pipe work, not a padded GEMM)
+            h = ops.stem_conv_in(x, mask, self.p["conv_in.weight"], self.p["conv_in.bias"], w3, self.p["encoder.conv_in.bias"])
+        elif self.mode == "tc" and "encoder.conv_in.padded" in self.wsplit and \
                 ops.tc_supported_conv(H, W, 64, self.p["encoder.conv_in.weight"].shape[0], 3, 1):
             xs = ops.stem_conv_split(x, mask, self.p["conv_in.weight"], self.p["conv_in.bias"], 64)
             h = ops.conv2d_tc(xs, self.wsplit["encoder.conv_in.padded"], self.p["encoder.conv_in.bias"], ksize=3,

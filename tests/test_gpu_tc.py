@@ -336,3 +336,26 @@ def test_subpixel_upsample_conv(ops, case):
     assert hasattr(y, "gn_partial")
     hi, lo = ops.groupnorm_split(y, ga.cuda(), be.cuda(), True)
     assert rel((hi.float() + lo.float()).permute(0, 3, 1, 2), gn) < 5e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 256), (1, 64, 64), (3, 16, 32), (1, 8, 4), (1, 128, 384)])
+def test_fused_stem_conv_in(ops, shape):
+    """cat(x, mask) -> 1x1 conv 5 -> 4 -> 3x3 conv 4 -> 128 (model.py:106-113, diffusionmodules/model.py:370) as one fp32 kernel
+    vs the two conv2d in fp64, and the GroupNorm statistics it leaves for the first ResnetBlock."""
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * 7 + W)
+    x = torch.randn(B, 4, H, W, generator=g)
+    mask = (torch.rand(B, 1, H, W, generator=g) < 0.3)
+    w1, b1 = torch.randn(4, 5, 1, 1, generator=g) * 0.5, torch.randn(4, generator=g)
+    w3, b3 = torch.randn(128, 4, 3, 3, generator=g) / 6, torch.randn(128, generator=g)
+    ga, be = torch.randn(128, generator=g), torch.randn(128, generator=g)
+    ref = F.conv2d(F.conv2d(torch.cat([x, mask.float()], 1).double(), w1.double(), b1.double()), w3.double(), b3.double(), padding=1)
+    y = ops.stem_conv_in(x.cuda(), mask.view(B, H, W).to(torch.uint8).cuda(), w1.view(4, 5).contiguous().cuda(), b1.cuda(),
+                         w3.permute(0, 2, 3, 1).reshape(128, 36).contiguous().cuda(), b3.cuda())
+    assert tuple(y.shape) == (B, H, W, 128) and rel(y.permute(0, 3, 1, 2), ref) < 2e-6
+    gn = F.group_norm(ref, 32, ga.double(), be.double(), eps=1e-6)
+    hi, lo = ops.groupnorm_split(y, ga.cuda(), be.cuda(), True)
+    assert rel((hi.float() + lo.float()).permute(0, 3, 1, 2), gn * torch.sigmoid(gn)) < 2e-5
+    y0 = ops.stem_conv_in(x.cuda(), None, w1.view(4, 5).contiguous().cuda(), b1.cuda(), w3.permute(0, 2, 3, 1).reshape(128, 36).contiguous().cuda(), b3.cuda(), gn_stats=False)
+    ref0 = F.conv2d(F.conv2d(torch.cat([x, torch.zeros(B, 1, H, W)], 1).double(), w1.double(), b1.double()), w3.double(), b3.double(), padding=1)
+    assert rel(y0.permute(0, 3, 1, 2), ref0) < 2e-6 and not hasattr(y0, "gn_partial")
