@@ -52,6 +52,32 @@ __device__ __forceinline__ float dot3(const float *a, float x0, float x1, float 
     return t;
 }
 
+#ifdef __CUDACC__
+// GroupNorm mean / rstd of batch element b from the S fp64 partial sums of gn_stats / splitk_reduce_stats
+// ([B][S][32 groups][sum, sumsq]) into shared memory; called by all 256 threads of a CTA, followed by __syncthreads().
+// Eight lanes per group stride over the splits and are combined by a fixed butterfly: with up to 128 splits a serial
+// loop by one thread per group was a chain of 128 dependent global loads in the prologue of EVERY CTA of the apply
+// kernels -- 17-25 us per launch on the small layers (ncu pass E), several times the kernel's own streaming time.
+__device__ __forceinline__ void gn_mean_rstd_from_partials(const double *__restrict__ partial, int b, int S, double n,
+                                                          float *mean_s, float *rstd_s) {
+    const int tid = threadIdx.x, g = tid >> 3, part = tid & 7;
+    double a = 0.0, q = 0.0;
+    for (int s = part; s < S; s += 8) {
+        const double2 v = *reinterpret_cast<const double2 *>(partial + (((size_t)b * S + s) * 32 + g) * 2);
+        a += v.x; q += v.y;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (part == 0) {
+        const double mean = a / n;
+        double var = q / n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        mean_s[g] = (float)mean;
+        rstd_s[g] = (float)(1.0 / sqrt(var + 1e-6));
+    }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  A frame is ~300 dependent kernels, many of them a few microseconds long, so
 // the launch / dependency-resolution latency between consecutive kernels is a visible share of a single-trajectory

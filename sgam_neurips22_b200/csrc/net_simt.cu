@@ -322,18 +322,7 @@ gn_apply_kernel(const float *__restrict__ x, const double *__restrict__ partial,
                 const float *__restrict__ beta, float *__restrict__ y, long long HW, int C, int S, int swish) {
     __shared__ float mean_s[32], rstd_s[32];
     const int b = blockIdx.y, tid = threadIdx.x;
-    if (tid < 32) {
-        double a = 0.0, q = 0.0;
-        for (int s = 0; s < S; ++s) {
-            const double *src = partial + (((size_t)b * S + s) * 32 + tid) * 2;
-            a += src[0]; q += src[1];
-        }
-        const double n = (double)HW * (C / 32), mean = a / n;
-        double var = q / n - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        mean_s[tid] = (float)mean;
-        rstd_s[tid] = (float)(1.0 / sqrt(var + 1e-6));
-    }
+    gn_mean_rstd_from_partials(partial, b, S, (double)HW * (C / 32), mean_s, rstd_s);
     __syncthreads();
     const int CQ = C / 4, cpg = C / 32;
     const long long total = HW * CQ;

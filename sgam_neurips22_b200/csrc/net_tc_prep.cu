@@ -43,17 +43,8 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
     const int b = blockIdx.y, tid = threadIdx.x;
     if (meanrstd) {                     // statistics already finalised (fused into the producing conv's epilogue)
         if (tid < 32) { mean_s[tid] = meanrstd[(b * 32 + tid) * 2]; rstd_s[tid] = meanrstd[(b * 32 + tid) * 2 + 1]; }
-    } else if (tid < 32) {
-        double a = 0.0, q = 0.0;
-        for (int s = 0; s < S; ++s) {
-            const double *src = partial + (((size_t)b * S + s) * 32 + tid) * 2;
-            a += src[0]; q += src[1];
-        }
-        const double n = (double)HW * (C / 32), mean = a / n;
-        double var = q / n - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        mean_s[tid] = (float)mean;
-        rstd_s[tid] = (float)(1.0 / sqrt(var + 1e-6));
+    } else {
+        gn_mean_rstd_from_partials(partial, b, S, (double)HW * (C / 32), mean_s, rstd_s);
     }
     __syncthreads();
     const int CO = C / 8, cpg = C / 32;                 // 8 channels per thread (cpg >= 4: at most two groups)
@@ -222,14 +213,17 @@ gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ meanrs
 // channels fill 3 % of an N = 128 tile, and the nine filter taps re-read the 128-channel operand nine times through L2
 // (round 1: 87 us of GroupNorm-apply + 341 us of GEMM at 14 TFLOP/s, L2-bound).  Here a CTA stages the normalised,
 // activated (8+2) x (16+2) x 128 halo tile in shared memory ONCE (zero padding applied after the activation, as the conv
-// sees it) and every warp reduces over the channels: lane l owns channels 4l..4l+3 (one GroupNorm group) with its
-// 9 x 4 x 4 filter taps in registers, walks segments of four neighbouring pixels (the 3 x 6 window is loaded once: 18
-// conflict-free 16-byte loads for 4 x 144 fused multiply-adds) and the sixteen per-lane partial sums of a segment are
-// combined over the 32 lanes by recursive halving (16 shuffles instead of 80).  FP32 FMA bound: 4608 FMAs per pixel.
+// sees it) and reduces over the channels on the FP32 pipes: lane l owns channels 4l..4l+3 (one GroupNorm group); the
+// eight warps form four PAIRS, a pair owns two rows of the tile and its two warps split the four output channels, so
+// each lane keeps 9 x 4 x 2 filter taps in registers (72, not 144: twice the resident warps) and no cross-warp sum is
+// needed.  A warp walks 2-row x 4-pixel segments: the 4 x 6 window is read once (24 conflict-free 16-byte loads for 576
+// fused multiply-adds) and the sixteen per-lane partial sums are combined over the 32 lanes by recursive halving (16
+// shuffles instead of 80).  4608 FMAs per output pixel: FP32-FMA bound.
 constexpr int HD_TH = 8, HD_TW = 16, HD_C = 128;
-constexpr int HD_SMEM = (HD_TH + 2) * (HD_TW + 2) * HD_C * 4;
+constexpr int HD_PIX = (HD_TH + 2) * (HD_TW + 2);
+constexpr int HD_SMEM = HD_PIX * HD_C * 4;
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 gn_head_conv_kernel(const float *__restrict__ x, const float *__restrict__ meanrstd, const float *__restrict__ gamma,
                     const float *__restrict__ beta, const float *__restrict__ w /* [9][128][4] */, const float *__restrict__ bias,
                     float *__restrict__ y /* [B][4][H][W] */, int H, int W) {
@@ -242,23 +236,23 @@ gn_head_conv_kernel(const float *__restrict__ x, const float *__restrict__ meanr
         const float mean = meanrstd[(b * 32 + lane) * 2], rstd = meanrstd[(b * 32 + lane) * 2 + 1];   // group = channel quad (128 / 32 = 4)
         const float4 ga = __ldg(reinterpret_cast<const float4 *>(gamma) + lane), be = __ldg(reinterpret_cast<const float4 *>(beta) + lane);
         const float4 *src = reinterpret_cast<const float4 *>(x) + (size_t)b * H * W * 32;
-        // 180 halo pixels, 45 per warp, in batches of 9 whose loads are all in flight before the first is used (a loop of
+        // 180 halo pixels over 8 warps, in batches of 8 whose loads are all in flight before the first is used (a loop of
         // load -> transform -> store exposed one full DRAM latency per pixel: 460 us for the layer, ncu pass E)
-        constexpr int PER_WARP = (HD_TH + 2) * (HD_TW + 2) / 4, BATCH = 9;
-        static_assert(PER_WARP * 4 == (HD_TH + 2) * (HD_TW + 2) && PER_WARP % BATCH == 0, "halo tile must split evenly");
+        constexpr int BATCH = 8;
 #pragma unroll 1
-        for (int b0 = 0; b0 < PER_WARP; b0 += BATCH) {
+        for (int b0 = 0; b0 < (HD_PIX + 7) / 8; b0 += BATCH) {
             float4 v[BATCH];
             bool ok[BATCH];
 #pragma unroll
             for (int i = 0; i < BATCH; ++i) {
-                const int pix = warp + 4 * (b0 + i);
+                const int pix = warp + 8 * (b0 + i);
                 const int gy = y0 - 1 + pix / (HD_TW + 2), gx = x0 - 1 + pix % (HD_TW + 2);
-                ok[i] = gy >= 0 && gy < H && gx >= 0 && gx < W;
+                ok[i] = pix < HD_PIX && gy >= 0 && gy < H && gx >= 0 && gx < W;
                 v[i] = ok[i] ? __ldg(src + ((size_t)gy * W + gx) * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int i = 0; i < BATCH; ++i) {
+                const int pix = warp + 8 * (b0 + i);
                 float4 t = v[i];
                 if (ok[i]) {
                     t.x = (t.x - mean) * rstd * ga.x + be.x; t.y = (t.y - mean) * rstd * ga.y + be.y;
@@ -266,42 +260,48 @@ gn_head_conv_kernel(const float *__restrict__ x, const float *__restrict__ meanr
                     t.x = __fdividef(t.x, 1.0f + __expf(-t.x)); t.y = __fdividef(t.y, 1.0f + __expf(-t.y));
                     t.z = __fdividef(t.z, 1.0f + __expf(-t.z)); t.w = __fdividef(t.w, 1.0f + __expf(-t.w));
                 }
-                hs[(warp + 4 * (b0 + i)) * 32 + lane] = t;
+                if (pix < HD_PIX) hs[pix * 32 + lane] = t;
             }
         }
     }
-    // ---- this lane's filter taps: wr[tap][channel of the quad] = the 4 output channels
-    float4 wr[9][4];
+    // ---- this lane's filter taps: wr[tap][channel of the quad] = output channels 2 op, 2 op + 1 (op = which warp of the pair)
+    const int pair = warp >> 1, op = warp & 1;
+    float2 wr[9][4];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) wr[t][c] = __ldg(reinterpret_cast<const float4 *>(w) + (t * HD_C + lane * 4 + c));
+        for (int c = 0; c < 4; ++c) wr[t][c] = __ldg(reinterpret_cast<const float2 *>(w) + ((t * HD_C + lane * 4 + c) * 2 + op));
     __syncthreads();
-    const float4 bo = __ldg(reinterpret_cast<const float4 *>(bias));
+    const float b0v = __ldg(bias + 2 * op), b1v = __ldg(bias + 2 * op + 1);
     const size_t plane = (size_t)H * W;
-    // warp -> rows 2 warp, 2 warp + 1 of the tile; segments of 4 pixels
+    // pair -> tile rows 2 pair, 2 pair + 1; segments of 2 rows x 4 pixels
 #pragma unroll 1
-    for (int seg = 0; seg < 2 * (HD_TW / 4); ++seg) {
-        const int ly = 2 * warp + seg / (HD_TW / 4), lx = (seg % (HD_TW / 4)) * 4;
-        float acc[16];                                              // [pixel 0..3][out 0..3]
+    for (int seg = 0; seg < HD_TW / 4; ++seg) {
+        const int ly = 2 * pair, lx = seg * 4;
+        float acc[16];                                              // [row 0..1][pixel 0..3][out 0..1]
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
+        for (int r = 0; r < 4; ++r) {                              // window row r feeds output row 0 as tap row r and output row 1 as tap row r - 1
             float4 xv[6];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) xv[j] = hs[((ly + kh) * (HD_TW + 2) + lx + j) * 32 + lane];
+            for (int j = 0; j < 6; ++j) xv[j] = hs[((ly + r) * (HD_TW + 2) + lx + j) * 32 + lane];
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int t = kh * 3 + kw;
+            for (int orow = 0; orow < 2; ++orow) {
+                const int kh = r - orow;
+                if (kh < 0 || kh > 2) continue;
 #pragma unroll
-                for (int px = 0; px < 4; ++px) {
-                    const float4 v = xv[px + kw];
-                    float *a = acc + 4 * px;
-                    a[0] = fmaf(v.x, wr[t][0].x, a[0]); a[1] = fmaf(v.x, wr[t][0].y, a[1]); a[2] = fmaf(v.x, wr[t][0].z, a[2]); a[3] = fmaf(v.x, wr[t][0].w, a[3]);
-                    a[0] = fmaf(v.y, wr[t][1].x, a[0]); a[1] = fmaf(v.y, wr[t][1].y, a[1]); a[2] = fmaf(v.y, wr[t][1].z, a[2]); a[3] = fmaf(v.y, wr[t][1].w, a[3]);
-                    a[0] = fmaf(v.z, wr[t][2].x, a[0]); a[1] = fmaf(v.z, wr[t][2].y, a[1]); a[2] = fmaf(v.z, wr[t][2].z, a[2]); a[3] = fmaf(v.z, wr[t][2].w, a[3]);
-                    a[0] = fmaf(v.w, wr[t][3].x, a[0]); a[1] = fmaf(v.w, wr[t][3].y, a[1]); a[2] = fmaf(v.w, wr[t][3].z, a[2]); a[3] = fmaf(v.w, wr[t][3].w, a[3]);
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int t = kh * 3 + kw;
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        const float4 v = xv[px + kw];
+                        float *a = acc + (orow * 4 + px) * 2;
+                        a[0] = fmaf(v.x, wr[t][0].x, a[0]); a[1] = fmaf(v.x, wr[t][0].y, a[1]);
+                        a[0] = fmaf(v.y, wr[t][1].x, a[0]); a[1] = fmaf(v.y, wr[t][1].y, a[1]);
+                        a[0] = fmaf(v.z, wr[t][2].x, a[0]); a[1] = fmaf(v.z, wr[t][2].y, a[1]);
+                        a[0] = fmaf(v.w, wr[t][3].x, a[0]); a[1] = fmaf(v.w, wr[t][3].y, a[1]);
+                    }
                 }
             }
         }
@@ -330,16 +330,12 @@ gn_head_conv_kernel(const float *__restrict__ x, const float *__restrict__ meanr
         }
         r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
         if ((lane & 1) == 0) {
-            const int v = lane >> 1, px = v >> 2, o = v & 3;      // v = 8 bit4 + 4 bit3 + 2 bit2 + bit1
-            const int gy = y0 + ly, gx = x0 + lx + px;
-            if (gy < H && gx < W) {
-                const float bv = o == 0 ? bo.x : (o == 1 ? bo.y : (o == 2 ? bo.z : bo.w));
-                y[((size_t)b * 4 + o) * plane + (size_t)gy * W + gx] = r1 + bv;
-            }
+            const int v = lane >> 1, orow = v >> 3, px = (v >> 1) & 3, o = v & 1;      // v = 8 bit4 + 4 bit3 + 2 bit2 + bit1
+            const int gy = y0 + ly + orow, gx = x0 + lx + px;
+            if (gy < H && gx < W) y[((size_t)b * 4 + 2 * op + o) * plane + (size_t)gy * W + gx] = r1 + (o ? b1v : b0v);
         }
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------ encoder stem
 // VQModel.encode's stem (cat(x, mask) -> 1x1 conv 5 -> 4, model.py:106-113) + encoder.conv_in (3x3, 4 -> 128,
@@ -526,7 +522,7 @@ extern "C" int sgam_gn_head_conv(const float *x, const float *gamma, const float
         SGAM_CUDA_OK(cudaFuncSetAttribute(gn_head_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM));
         configured = true;
     }
-    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_head_conv_kernel, dim3(cdiv(W, HD_TW), cdiv(H, HD_TH), B), 128, HD_SMEM, s, x, meanrstd, gamma, beta, w_t, bias, y, H, W);
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_head_conv_kernel, dim3(cdiv(W, HD_TW), cdiv(H, HD_TH), B), 256, HD_SMEM, s, x, meanrstd, gamma, beta, w_t, bias, y, H, W);
     return SGAM_OK;
 }
 
