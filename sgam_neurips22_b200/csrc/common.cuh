@@ -62,9 +62,15 @@ __device__ __forceinline__ void gn_mean_rstd_from_partials(const double *__restr
                                                           float *mean_s, float *rstd_s) {
     const int tid = threadIdx.x, g = tid >> 3, part = tid & 7;
     double a = 0.0, q = 0.0;
-    for (int s = part; s < S; s += 8) {
-        const double2 v = *reinterpret_cast<const double2 *>(partial + (((size_t)b * S + s) * 32 + g) * 2);
-        a += v.x; q += v.y;
+    for (int s0 = 0; s0 < S; s0 += 128) {               // S <= 128 in practice: one round, all 16 loads in flight at once
+        double2 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int s = s0 + part + 8 * i;
+            v[i] = s < S ? __ldg(reinterpret_cast<const double2 *>(partial + (((size_t)b * S + s) * 32 + g) * 2)) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { a += v[i].x; q += v[i].y; }
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }

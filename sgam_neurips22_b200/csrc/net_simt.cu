@@ -446,7 +446,8 @@ extern "C" int sgam_gemm_nt(const float *A, const float *Bm, float *C, const flo
 }
 
 extern "C" int sgam_gn_splits(long long HW) {
-    long long s = HW / 8;               // >= 8 pixels per block, at most 128 blocks per batch element
+    long long s = HW / 2;               // >= 2 pixels per block, at most 128 blocks per batch element: the statistics / split-K
+                                        // reduce kernels of the 16 x 16 layers are latency chains, so more, shorter blocks win
     return (int)(s < 1 ? 1 : (s > 128 ? 128 : s));
 }
 

@@ -51,25 +51,37 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
     const long long total = HW * CO;
     const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)b * HW * C);
     uint4 *dh = reinterpret_cast<uint4 *>(hi + (size_t)b * HW * C), *dl = reinterpret_cast<uint4 *>(lo + (size_t)b * HW * C);
-    for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(e % CO) * 8, g0 = c / cpg, g1 = (c + 4) / cpg;
-        const float mu0 = mean_s[g0], rs0 = rstd_s[g0], mu1 = mean_s[g1], rs1 = rstd_s[g1];
-        const float4 v0 = __ldg(src + 2 * e), v1 = __ldg(src + 2 * e + 1);
-        const float4 ga0 = __ldg(reinterpret_cast<const float4 *>(gamma + c)), ga1 = __ldg(reinterpret_cast<const float4 *>(gamma + c + 4));
-        const float4 be0 = __ldg(reinterpret_cast<const float4 *>(beta + c)), be1 = __ldg(reinterpret_cast<const float4 *>(beta + c + 4));
-        float o[8] = {(v0.x - mu0) * rs0 * ga0.x + be0.x, (v0.y - mu0) * rs0 * ga0.y + be0.y,
-                      (v0.z - mu0) * rs0 * ga0.z + be0.z, (v0.w - mu0) * rs0 * ga0.w + be0.w,
-                      (v1.x - mu1) * rs1 * ga1.x + be1.x, (v1.y - mu1) * rs1 * ga1.y + be1.y,
-                      (v1.z - mu1) * rs1 * ga1.z + be1.z, (v1.w - mu1) * rs1 * ga1.w + be1.w};
-        if (swish) {
+    // 4 independent 8-channel groups per thread and iteration, all 8 loads issued before the first is used
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e0 = (long long)blockIdx.x * blockDim.x + tid; e0 < total; e0 += 4 * stride) {
+        float4 v0[4], v1[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = __fdividef(o[k], 1.0f + __expf(-o[k]));   // <= 3 ulp; keeps the kernel HBM-bound
+        for (int u = 0; u < 4; ++u) {
+            const long long e = e0 + u * stride;
+            if (e < total) { v0[u] = __ldg(src + 2 * e); v1[u] = __ldg(src + 2 * e + 1); }
         }
-        uint32_t h[4], l[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) split2(o[2 * k], o[2 * k + 1], h[k], l[k]);
-        dh[e] = make_uint4(h[0], h[1], h[2], h[3]);
-        dl[e] = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int u = 0; u < 4; ++u) {
+            const long long e = e0 + u * stride;
+            if (e >= total) break;
+            const int c = (int)(e % CO) * 8, g0 = c / cpg, g1 = (c + 4) / cpg;
+            const float mu0 = mean_s[g0], rs0 = rstd_s[g0], mu1 = mean_s[g1], rs1 = rstd_s[g1];
+            const float4 ga0 = __ldg(reinterpret_cast<const float4 *>(gamma + c)), ga1 = __ldg(reinterpret_cast<const float4 *>(gamma + c + 4));
+            const float4 be0 = __ldg(reinterpret_cast<const float4 *>(beta + c)), be1 = __ldg(reinterpret_cast<const float4 *>(beta + c + 4));
+            float o[8] = {(v0[u].x - mu0) * rs0 * ga0.x + be0.x, (v0[u].y - mu0) * rs0 * ga0.y + be0.y,
+                          (v0[u].z - mu0) * rs0 * ga0.z + be0.z, (v0[u].w - mu0) * rs0 * ga0.w + be0.w,
+                          (v1[u].x - mu1) * rs1 * ga1.x + be1.x, (v1[u].y - mu1) * rs1 * ga1.y + be1.y,
+                          (v1[u].z - mu1) * rs1 * ga1.z + be1.z, (v1[u].w - mu1) * rs1 * ga1.w + be1.w};
+            if (swish) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = __fdividef(o[k], 1.0f + __expf(-o[k]));   // <= 3 ulp; keeps the kernel HBM-bound
+            }
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split2(o[2 * k], o[2 * k + 1], h[k], l[k]);
+            dh[e] = make_uint4(h[0], h[1], h[2], h[3]);
+            dl[e] = make_uint4(l[0], l[1], l[2], l[3]);
+        }
     }
 }
 
@@ -426,6 +438,15 @@ stem_conv_in_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mas
 
 }  // namespace
 
+// CTAs per image of gn_apply_split_kernel: each thread should own ~4 8-channel groups (one unrolled iteration) and the
+// whole launch should not exceed ~8 CTAs per SM; small tensors get fewer CTAs rather than one group per thread
+static unsigned gn_apply_blocks(long long total, int B) {
+    long long want = (total + 1023) / 1024;                          // 256 threads x 4 groups
+    const long long cap = ((long long)148 * 8 + B - 1) / B;
+    if (want > cap) want = cap;
+    return (unsigned)(want < 1 ? 1 : want);
+}
+
 // gn_stats launcher lives in net_simt.cu
 int sgam_gn_stats_launch(const float *x, double *partial, int B, long long HW, int C, cudaStream_t s);
 
@@ -454,7 +475,7 @@ extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const fl
     int rc = sgam_gn_stats_launch(x, partial, B, HW, C, s);
     if (rc) return rc;
     const long long total = HW * (C / 8);
-    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
+    const unsigned blocks = gn_apply_blocks(total, B);
     SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
                                                           sgam_gn_splits(HW), swish);
     return SGAM_OK;
@@ -465,7 +486,7 @@ extern "C" int sgam_groupnorm_split_apply(const float *x, const float *gamma, co
     SGAM_REQUIRE(x && gamma && beta && hi && lo && partial, "groupnorm_split_apply: null pointer");
     SGAM_REQUIRE(B > 0 && HW > 0 && C % 128 == 0 && C <= 1024, "groupnorm_split_apply: C=%d must be a multiple of 128 (<= 1024)", C);
     const long long total = HW * (C / 8);
-    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
+    const unsigned blocks = gn_apply_blocks(total, B);
     SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, (cudaStream_t)stream, x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
                                                                              sgam_gn_splits(HW), swish);
     return SGAM_OK;
@@ -488,7 +509,7 @@ extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, co
     float *meanrstd = gn_partial + (long long)B * tiles * 64;
     SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_finalize_kernel, cdiv(B * 32, 8), 256, 0, s, gn_partial, meanrstd, tiles, (double)HW * (C / 32), B * 32);
     const long long total = HW * (C / 8);
-    const unsigned blocks = (unsigned)min((long long)148 * 8, (total + 255) / 256);
+    const unsigned blocks = gn_apply_blocks(total, B);
     SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
     return SGAM_OK;
 }

@@ -34,7 +34,7 @@ def test_argument_validation_without_gpu():
     assert b"vq_nearest" in lib.sgam_last_error()
     assert lib.sgam_conv2d(None, None, None, None, None, 1, 8, 8, 4, 4, 3, 1, 0, 0, 0, None) == -1
     assert lib.sgam_splat_workspace_bytes(2, 16, 16) == 2 * 16 * 16 * 8
-    assert lib.sgam_gn_splits(65536) == 128 and lib.sgam_gn_splits(16) == 2 and lib.sgam_gn_splits(4) == 1
+    assert lib.sgam_gn_splits(65536) == 128 and lib.sgam_gn_splits(16) == 8 and lib.sgam_gn_splits(4) == 2 and lib.sgam_gn_splits(1) == 1
 
 
 def test_ops_refuse_cpu_tensors():

@@ -22,6 +22,23 @@ ya = ops.conv2d_tc(ops.split_bf16(xa), ops.split_weight(wa, pad_rows_to=32), tor
 hi_a, lo_a = ops.groupnorm_split(ya, torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"), True)
 torch.cuda.synchronize()
 print("swap ok", float(ya.double().sum()), float(hi_a.float().abs().mean()))
+# round-2 kernels: fused attention (2 pair tiles x 4 key tiles), sub-pixel Upsample (swap + pair kernels), fused stem / head
+qa, ka, va = (torch.randn(2, 512, 256, generator=g).cuda() for _ in range(3))
+oa = ops.attention_tc(ops.split_weight(qa), ops.split_weight(ka), ops.split_weight(va.transpose(1, 2).contiguous()), 256 ** -0.5)
+torch.cuda.synchronize()
+print("attn ok", float((oa[0].float() + oa[1].float()).double().sum()))
+for (Bu, Hu, Cu, Co) in ((3, 128, 128, 128), (5, 64, 256, 256)):
+    xu = torch.randn(Bu, Hu, Hu, Cu, generator=g).cuda()
+    wu = (torch.randn(Co, 9 * Cu, generator=g) * 0.03).cuda()
+    yu = ops.conv2d_tc_up2(ops.split_bf16(xu), ops.split_weight(ops.subpixel_weights(wu, Cu)), torch.zeros(Co, device="cuda"))
+    hu, lu = ops.groupnorm_split(yu, torch.ones(Co, device="cuda"), torch.zeros(Co, device="cuda"), True)
+    torch.cuda.synchronize()
+    print("up2 ok", float(yu.double().sum()), float(hu.float().abs().mean()))
+xs_ = torch.randn(1, 4, 64, 64, generator=g).cuda()
+ys_ = ops.stem_conv_in(xs_, None, torch.randn(4, 5, generator=g).cuda(), torch.randn(4, generator=g).cuda(), (torch.randn(128, 36, generator=g) / 6).cuda(), torch.randn(128, generator=g).cuda())
+yh_ = ops.gn_head_conv(ys_, torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"), (torch.randn(9, 128, 4, generator=g) * 0.03).cuda(), torch.zeros(4, device="cuda"))
+torch.cuda.synchronize()
+print("stem/head ok", float(ys_.double().sum()), float(yh_.double().sum()))
 # RGB-D integration kernels on a small volume
 from sgam_neurips22_b200.tsdf import TSDFVolume, frustum_box
 K = np.array([[124.4, 0, 32.0], [0, 124.4, 32.0], [0, 0, 1.0]])
@@ -39,8 +56,8 @@ import hashlib
 print("step ok", float(decs[0][0].abs().mean()), hashlib.sha256(decs[0][0].cpu().numpy().tobytes()).hexdigest()[:16])
 PY
 echo "=== plain run (the sanitizer runs must reproduce this checksum) ==="
-python /tmp/san_step.py 2>&1 | grep -E "step ok|tsdf ok|swap ok"
+python /tmp/san_step.py 2>&1 | grep -E "step ok|tsdf ok|swap ok|attn ok|up2 ok|stem/head ok"
 for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
   echo "=== compute-sanitizer --tool $tool ==="
-  timeout -s KILL 900 compute-sanitizer --tool $tool python /tmp/san_step.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|step ok|tsdf ok|swap ok|Error|hazard" | head -8
+  timeout -s KILL 900 compute-sanitizer --tool $tool python /tmp/san_step.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|step ok|tsdf ok|swap ok|attn ok|up2 ok|stem/head ok|Error|hazard" | head -14
 done
