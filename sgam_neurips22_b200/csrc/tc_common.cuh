@@ -192,21 +192,22 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
     __syncwarp();
     es.rowoff[q][lane] = row_ok ? row_off : -1;
     __syncwarp();
-    if (p.vq_tilemin) {                               // codebook search: per-row minimum of the approximate distances
-        const float zz = row_ok ? __ldg(p.vq_zz + m) : 0.0f;
-        float best = INFINITY;
+    if (p.vq_tilemin) {                               // codebook search: per-row minima of the approximate distances, one per
+        const float zz = row_ok ? __ldg(p.vq_zz + m) : 0.0f;                     // 32-code sub-tile (the refinement re-evaluates whole
+        float *dst = p.vq_tilemin + (m * p.tiles_n + n_tile) * (BN / 32);        // sub-tiles: finer ones = fewer exact distances)
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_acc + (uint32_t)c0, v);
+            float best = INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 e4 = __ldg(reinterpret_cast<const float4 *>(p.vq_ee + n0 + c0 + j));
                 best = fminf(best, fminf(fminf((zz + e4.x) - 2.0f * __uint_as_float(v[j]), (zz + e4.y) - 2.0f * __uint_as_float(v[j + 1])),
                                          fminf((zz + e4.z) - 2.0f * __uint_as_float(v[j + 2]), (zz + e4.w) - 2.0f * __uint_as_float(v[j + 3]))));
             }
+            if (row_ok) dst[c0 / 32] = best;
         }
-        if (row_ok) p.vq_tilemin[m * p.tiles_n + n_tile] = best;
         return;
     }
     if (p.ksplit > 1) {                               // raw partial sums; bias / residual / statistics happen in the reduce kernel

@@ -119,39 +119,42 @@ vq_norms_kernel(const float *__restrict__ x, float *__restrict__ out, int rows, 
     out[r] = s;
 }
 
-// Exact phase of the tensor-core search.  One CTA per token: find the tiles whose approximate minimum is within
+// Exact phase of the tensor-core search.  One CTA per token: find the 32-code sub-tiles whose approximate minimum is within
 // `slack` of the best one (the canonical arg-min is provably among them when slack >= 2 * max |d_approx - d_canonical|),
-// re-evaluate their 128 codes each in the canonical fp32 order, take the first arg-min, gather the code vector.
-constexpr int VQ_TILE = 128;
+// re-evaluate their codes in the canonical fp32 order -- one warp per candidate sub-tile, lane = code -- take the first
+// arg-min, gather the code vector.  (Round 1 kept one minimum per 128-code GEMM tile and re-evaluated 128 codes per
+// candidate with one thread per code: 4x the exact distances and 128 KB of codebook per candidate through L1.)
+constexpr int VQ_TILE = 128;                      // column tile of the distance GEMM
+constexpr int VQ_SUB = 32;                        // codes per sub-tile minimum
 __global__ void __launch_bounds__(VQ_TILE)
 vq_refine_kernel(const float *__restrict__ z, const float *__restrict__ E, const float *__restrict__ zz, const float *__restrict__ ee,
-                 const float *__restrict__ tilemin, float ee_max, float slack_rel, int n_tiles, int D,
+                 const float *__restrict__ submin, float ee_max, float slack_rel, int n_sub, int D,
                  int64_t *__restrict__ idx, float *__restrict__ z_q, float *__restrict__ dmin) {
     extern __shared__ float zs[];                     // [D] token, then the candidate list
     __shared__ float red_f[4];
     __shared__ unsigned long long red_k[4];
     __shared__ int n_cand;
-    int *cand = reinterpret_cast<int *>(zs + D);      // [n_tiles]
+    int *cand = reinterpret_cast<int *>(zs + D);      // [n_sub]
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < D; k += VQ_TILE) zs[k] = z[(size_t)t * D + k];
     if (tid == 0) n_cand = 0;
     float m = INFINITY;
-    for (int i = tid; i < n_tiles; i += VQ_TILE) m = fminf(m, tilemin[(size_t)t * n_tiles + i]);
+    for (int i = tid; i < n_sub; i += VQ_TILE) m = fminf(m, submin[(size_t)t * n_sub + i]);
     for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) red_f[warp] = m;
     __syncthreads();
     m = fminf(fminf(red_f[0], red_f[1]), fminf(red_f[2], red_f[3]));
     const float zzt = zz[t];
     const float thr = m + slack_rel * (zzt + ee_max);
-    // NaN-safe: a NaN / inf latent makes every tile minimum (and thr) NaN or inf; `!(x > thr)` then keeps EVERY tile, so
+    // NaN-safe: a NaN / inf latent makes every minimum (and thr) NaN or inf; `!(x > thr)` then keeps EVERY sub-tile, so
     // such a row is re-evaluated exhaustively and gets exactly the canonical kernel's answer instead of an empty list
-    for (int i = tid; i < n_tiles; i += VQ_TILE)
-        if (!(tilemin[(size_t)t * n_tiles + i] > thr)) cand[atomicAdd(&n_cand, 1)] = i;
+    for (int i = tid; i < n_sub; i += VQ_TILE)
+        if (!(submin[(size_t)t * n_sub + i] > thr)) cand[atomicAdd(&n_cand, 1)] = i;
     __syncthreads();
     unsigned long long key = ~0ull;
     const int nc = n_cand;
-    for (int ci = 0; ci < nc; ++ci) {
-        const int c = cand[ci] * VQ_TILE + tid;
+    for (int ci = warp; ci < nc; ci += VQ_TILE / 32) {                 // the list order varies, the minimum over it does not
+        const int c = cand[ci] * VQ_SUB + lane;
         const float4 *ev = reinterpret_cast<const float4 *>(E + (size_t)c * D);
         float dot = 0.0f;
         for (int k = 0; k < D / 4; ++k) {
@@ -172,7 +175,7 @@ vq_refine_kernel(const float *__restrict__ z, const float *__restrict__ E, const
     key = red_k[0];
     for (int w = 1; w < 4; ++w) key = red_k[w] < key ? red_k[w] : key;
     unsigned e = (unsigned)(key & 0xffffffffull);
-    if (e >= (unsigned)(n_tiles * VQ_TILE)) e = 0;     // cannot happen with the NaN-safe candidate test; never index out of the codebook
+    if (e >= (unsigned)(n_sub * VQ_SUB)) e = 0;        // cannot happen with the NaN-safe candidate test; never index out of the codebook
     if (tid == 0) {
         idx[t] = (int64_t)e;
         if (dmin) dmin[t] = orderable_float((uint32_t)(key >> 32));
@@ -304,7 +307,7 @@ extern "C" int sgam_vq_norms(const float *x, float *out, int rows, int D, void *
     return SGAM_OK;
 }
 
-extern "C" size_t sgam_vq_tc_workspace_bytes(int T, int n_e) { return ((size_t)T * (n_e / VQ_TILE) + (size_t)T) * sizeof(float); }
+extern "C" size_t sgam_vq_tc_workspace_bytes(int T, int n_e) { return ((size_t)T * (n_e / VQ_SUB) + (size_t)T) * sizeof(float); }
 
 extern "C" int sgam_vq_nearest_tc(const float *z, const void *z_hi, const void *z_lo, const float *codebook, const void *e_hi,
                                   const void *e_lo, const float *ee, float ee_max, int T, int n_e, int D, void *workspace,
@@ -312,15 +315,15 @@ extern "C" int sgam_vq_nearest_tc(const float *z, const void *z_hi, const void *
     SGAM_REQUIRE(z && z_hi && z_lo && codebook && e_hi && e_lo && ee && workspace && idx && z_q, "vq_nearest_tc: null pointer");
     SGAM_REQUIRE(T > 0 && n_e > 0 && D % 64 == 0 && n_e % VQ_TILE == 0, "vq_nearest_tc: needs D %% 64 == 0 and n_e %% 128 == 0 (D=%d n_e=%d)", D, n_e);
     cudaStream_t s = (cudaStream_t)stream;
-    float *tilemin = (float *)workspace, *zz = tilemin + (size_t)T * (n_e / VQ_TILE);
+    float *tilemin = (float *)workspace, *zz = tilemin + (size_t)T * (n_e / VQ_SUB);
     vq_norms_kernel<<<cdiv(T, 128), 128, 0, s>>>(z, zz, T, D);
     SGAM_LAUNCH_OK();
     int rc = sgam_vq_tilemin_launch(z_hi, z_lo, e_hi, e_lo, zz, ee, tilemin, T, n_e, D, s);
     if (rc) return rc;
     // |d_tc - d_canonical| <= 2 * (2^-15 + 256 * 2^-24) * |z||e| <= 1e-4 * (|z|^2 + |e|^2)/2 ; slack = 2 * that bound
-    const int n_tiles = n_e / VQ_TILE;
-    const size_t smem = (size_t)D * sizeof(float) + (size_t)n_tiles * sizeof(int);
-    vq_refine_kernel<<<T, VQ_TILE, smem, s>>>(z, codebook, zz, ee, tilemin, ee_max, 1e-4f, n_tiles, D, idx, z_q, dmin);
+    const int n_sub = n_e / VQ_SUB;
+    const size_t smem = (size_t)D * sizeof(float) + (size_t)n_sub * sizeof(int);
+    vq_refine_kernel<<<T, VQ_TILE, smem, s>>>(z, codebook, zz, ee, tilemin, ee_max, 1e-4f, n_sub, D, idx, z_q, dmin);
     SGAM_LAUNCH_OK();
     return SGAM_OK;
 }
