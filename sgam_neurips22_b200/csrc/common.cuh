@@ -82,6 +82,32 @@ __device__ __forceinline__ void gn_mean_rstd_from_partials(const double *__restr
         rstd_s[g] = (float)(1.0 / sqrt(var + 1e-6));
     }
 }
+// The same from the fp32 per-pixel-block sums the GEMM epilogues emit ([B][tiles][32 groups][sum, sumsq]); for tensors of at
+// most 64 blocks per image the apply kernel finalises them itself instead of waiting for a separate 6 us launch.
+__device__ __forceinline__ void gn_mean_rstd_from_tiles(const float *__restrict__ tile_partial, int b, int tiles, double n,
+                                                       float *mean_s, float *rstd_s) {
+    const int tid = threadIdx.x, g = tid >> 3, part = tid & 7;
+    double a = 0.0, q = 0.0;
+    for (int t0 = 0; t0 < tiles; t0 += 64) {
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = t0 + part + 8 * i;
+            v[i] = t < tiles ? __ldg(reinterpret_cast<const float2 *>(tile_partial + (((size_t)b * tiles + t) * 32 + g) * 2)) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += (double)v[i].x; q += (double)v[i].y; }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (part == 0) {
+        const double mean = a / n;
+        double var = q / n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        mean_s[g] = (float)mean;
+        rstd_s[g] = (float)(1.0 / sqrt(var + 1e-6));
+    }
+}
 #endif
 
 // ------------------------------------------------------------------------------------------------

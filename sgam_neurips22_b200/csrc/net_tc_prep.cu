@@ -41,7 +41,9 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
     SGAM_PDL_PROLOGUE();
     __shared__ float mean_s[32], rstd_s[32];
     const int b = blockIdx.y, tid = threadIdx.x;
-    if (meanrstd) {                     // statistics already finalised (fused into the producing conv's epilogue)
+    if (meanrstd && S > 0) {            // per-pixel-block sums from the producing conv's epilogue, S = blocks per image (<= 64)
+        gn_mean_rstd_from_tiles(meanrstd, b, S, (double)HW * (C / 32), mean_s, rstd_s);
+    } else if (meanrstd) {              // statistics already finalised by gn_finalize_kernel
         if (tid < 32) { mean_s[tid] = meanrstd[(b * 32 + tid) * 2]; rstd_s[tid] = meanrstd[(b * 32 + tid) * 2 + 1]; }
     } else {
         gn_mean_rstd_from_partials(partial, b, S, (double)HW * (C / 32), mean_s, rstd_s);
@@ -506,10 +508,14 @@ extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, co
     const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
     const int tiles = cdiv(Wo, BW) * cdiv(Ho, BH);
     const long long HW = (long long)Ho * Wo;
-    float *meanrstd = gn_partial + (long long)B * tiles * 64;
-    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_finalize_kernel, cdiv(B * 32, 8), 256, 0, s, gn_partial, meanrstd, tiles, (double)HW * (C / 32), B * 32);
     const long long total = HW * (C / 8);
     const unsigned blocks = gn_apply_blocks(total, B);
+    if (tiles <= 64) {                  // few blocks per image: every CTA of the apply kernel finalises the sums itself (one launch less)
+        SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, nullptr, gn_partial, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, tiles, swish);
+        return SGAM_OK;
+    }
+    float *meanrstd = gn_partial + (long long)B * tiles * 64;
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_finalize_kernel, cdiv(B * 32, 8), 256, 0, s, gn_partial, meanrstd, tiles, (double)HW * (C / 32), B * 32);
     SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
     return SGAM_OK;
 }
