@@ -165,3 +165,24 @@ def test_vqmodel_forward_graph_replay_equals_eager(models):
         assert tuple(r[0][0].shape) == (1, 1, 4, 64, 64) and tuple(r[3].shape) == (1, 1, 256, 4, 4)
     dec_plain, loss = model(xs[0], extrapolation_mask=ms[0])               # topk=None signature (config 1): [dec, emb_loss]
     assert torch.equal(dec_plain, eager[0][0][0][0]) and loss.dim() == 0
+
+
+def test_get_x_returns_the_coded_target_like_the_reference(models):
+    """model.py:238: get_x always returns x_dst = cat(dst_img, coded dst_depth); only the scene loop's all-zero placeholders
+    (marked `_dst_placeholder` by prepare_batch_data) skip that work."""
+    from sgam_neurips22_b200 import synthetic
+    ds = "clevr-infinite"
+    model = models(ds)
+    b = synthetic.scene_step_batch(ds, res=64, batch=2, seed=1)
+    rng = np.random.default_rng(2)
+    b["dst_img"] = rng.uniform(-1, 1, (2, 64, 64, 3)).astype(np.float32)
+    b["dst_depth"] = rng.uniform(7, 16, (2, 64, 64)).astype(np.float32)
+    batch = {k: torch.from_numpy(v) for k, v in b.items()}
+    x, x_dst = model.get_x(dict(batch), ds)
+    x2, x_dst2, mask, wd = model.get_x(dict(batch), ds, return_extrapolation_mask=True, no_depth_range=True)
+    assert torch.equal(x, x2) and torch.equal(x_dst, x_dst2) and tuple(x_dst.shape) == (2, 4, 64, 64)
+    inv = (1 / torch.from_numpy(b["dst_depth"]) - 1 / 16) / (1 / 7 - 1 / 16)
+    ref = torch.cat([torch.from_numpy(b["dst_img"]).permute(0, 3, 1, 2), (2 * inv - 1)[:, None]], 1)
+    assert torch.allclose(x_dst.cpu(), ref, atol=1e-6)
+    batch["_dst_placeholder"] = True
+    assert model.get_x(dict(batch), ds, return_extrapolation_mask=True, no_depth_range=True)[1] is None

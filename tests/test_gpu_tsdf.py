@@ -152,3 +152,52 @@ def test_empty_frame_and_empty_cloud():
     assert float(dev.render_depth(K, np.eye(4), H, W, z_far=4.0).abs().sum()) == 0.0
     xyz, col = dev.extract_point_cloud()
     assert tuple(xyz.shape) == (0, 3) and tuple(col.shape) == (0, 3)
+
+
+def test_unit_pool_exhaustion_drops_units_instead_of_faulting():
+    """The voxel data lives in a bounded pool behind a page table (<= max_bytes per trajectory).  When the pool runs out the
+    remaining units stay closed: nothing is written out of bounds, the dropped units are counted, the opened ones keep
+    their exact values, and ray casting / extraction still work."""
+    from sgam_neurips22_b200.tsdf import TSDFVolume, frustum_box
+    frames = scene(4, n_frames=2)
+    lo, hi = frustum_box(K, [f[2] for f in frames], H, W, 3.3, pad=0.2)
+    full = TSDFVolume(0.01, 0.03, lo, hi, with_color=False)
+    for depth, rgb, T in frames:
+        full.integrate(torch.from_numpy(depth).cuda(), None, K, T)
+    need = full.units_in_use()
+    assert need > 100 and full.dropped_units() == 0 and full.memory_bytes() < full.page.numel() * 4096 * 8
+    small = TSDFVolume(0.01, 0.03, lo, hi, with_color=False, max_bytes=(need // 2) * 4096 * 8)
+    assert small.capacity == need // 2
+    for depth, rgb, T in frames:
+        small.integrate(torch.from_numpy(depth).cuda(), None, K, T)
+    torch.cuda.synchronize()
+    assert small.units_in_use() == small.capacity and small.dropped_units() > 0
+    assert int((small.page > 0).sum()) == small.capacity and int(small.page.max()) == small.capacity
+    d = small.render_depth(K, frames[0][2], H, W, z_far=4.0)
+    assert bool(torch.isfinite(d).all())
+    xyz, _ = small.extract_point_cloud()
+    assert 0 < xyz.shape[0] < full.extract_point_cloud()[0].shape[0]
+
+
+def test_integrate_once_is_a_switch_and_the_default_reintegrates(tmp_path, monkeypatch):
+    """inference_pipeline.py:771-777 fuses every selected source at every step (default here too); integrate_once=True fuses a
+    frame only the first time it is selected: the volume then holds weight 1 where the default holds the selection count."""
+    from sgam_neurips22_b200 import synthetic
+    from sgam_neurips22_b200.inference_pipeline import InfiniteSceneGeneration
+    from sgam_neurips22_b200.model import VQModel
+    monkeypatch.chdir(tmp_path)
+    ds = "google_earth"
+    model = synthetic.randomize_weights(VQModel(**synthetic.model_kwargs(ds)), seed=0).to("cuda:0").eval()
+    rng = np.random.default_rng(5)
+    yy, xx = np.meshgrid(np.linspace(0, 1, 256), np.linspace(0, 1, 256), indexing="ij")
+    seed = (rng.integers(0, 256, (256, 256, 3)).astype(np.uint8), (2.0 + 0.5 * np.sin(3 * xx) * np.cos(2 * yy)).astype(np.float32))
+    wmax = {}
+    for once in (False, True):
+        pipe = InfiniteSceneGeneration(model, ds, seed_frame=seed, output_dim=(4, 1), use_rgbd_integration=True, integrate_once=once,
+                                       output_root=str(tmp_path / f"once{int(once)}"))
+        for _ in range(3):
+            pipe.one_step_prediction(pipe.next_pose(pipe.curr), save_res_to_disk=False)
+            pipe.curr += 1
+        wmax[once] = float(pipe.volume.pool_vol[..., 1].max())
+        assert pipe.volume.dropped_units() == 0
+    assert wmax[True] <= 3.0 and wmax[False] > wmax[True]          # 3 frames fused once each vs the seed fused at every step
