@@ -210,15 +210,6 @@ int pick_bn(long long tiles_m, int N, int num_kb) {
     // by L2 -> SMEM bandwidth (ncu: 453 MB per launch at 9.6 TB/s, tensor pipe 35 %).  128-wide tiles with a 2-way
     // split-K launch as many CTAs and move a third less.
     if (num_kb >= 16) {
-        // ... and where the K loop is long enough to be split four ways, 256-wide tiles with a 4-way split-K move another
-        // quarter less (A: 32 KB + B: 64 KB per 1536 MMA cycles instead of 32 + 32 per 768): 512-channel 3x3 convs at 16x16
-        // with 8 trajectories.  SGAM_TC_WIDE_SPLITK=0 disables it (experiment knob).
-        static int wide = -1;
-        if (wide < 0) { const char *e = getenv("SGAM_TC_WIDE_SPLITK"); wide = e ? atoi(e) : 1; }
-        if (wide && N % 256 == 0 && num_kb >= 32 && tiles_m >= 8) {
-            const long long t256 = tiles_m * (N / 256);
-            if (4 * t256 <= sms && 8 * t256 > sms) return 256;
-        }
         const long long t = tiles_m * (N / 128);
         if (2 * t <= sms && 4 * t > sms) return 128;
     }
