@@ -364,8 +364,13 @@ extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize
 extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                               const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
                               int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws,
-                              double *splitk_gn_partial, void *stream) {
+                              double *splitk_gn_partial, int *host_stats_written, void *stream) {
     SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && (y || (y_hi && y_lo)), "conv2d_tc: null pointer");
+    // which GroupNorm statistics this call produces (the caller must not guess the kernel choice): 0 none, 1 the fp32
+    // per-pixel-block sums in gn_partial (every unsplit path), 2 the fp64 sums in splitk_gn_partial (split-K + reduce)
+    int stats_dummy = 0;
+    int &stats_written = host_stats_written ? *host_stats_written : stats_dummy;
+    stats_written = gn_partial ? 1 : 0;
     SGAM_REQUIRE(!gn_partial || (Cout % 128 == 0 && Cout <= 512 && !out_nchw), "conv2d_tc: fused GroupNorm statistics need Cout in {128,256,384,512}");
     SGAM_REQUIRE(stride == 1 || stride == 2, "conv2d_tc: stride %d", stride);
     const int Ho = H / stride, Wo = W / stride;        // stride 1: same; stride 2: pad (0,1,0,1) then 3x3/2 -> H/2 (even H)
@@ -432,6 +437,7 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
         if (rc2) return rc2;
         const long long total_q = p.split_stride / 4;
         if (splitk_gn_partial && Cout % 128 == 0 && Cout <= 1024) {          // reduction + GroupNorm statistics in one pass
+            stats_written = 2;
             const long long HW = (long long)Ho * Wo;
             const int S = sgam_gn_splits(HW);
             SGAM_PDL_LAUNCH(SGAM_PDL_MISC, splitk_reduce_stats_kernel, dim3(S, B), 256, 0, (cudaStream_t)stream, splitk_ws, p.split_stride, p.ksplit, bias, residual, y,

@@ -4,6 +4,8 @@ PyTorch is plumbing here: it owns the device memory and the stream; every functi
 allocates the outputs and enqueues the library's kernels on `torch.cuda.current_stream()`.  Nothing falls
 back to ATen: a missing library or a CPU tensor raises.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -438,12 +440,15 @@ def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=
                 partial64 = torch.empty(B * lib.sgam_gn_splits(Ho * Wo) * 64, dtype=torch.float64, device=x_hi.device)
     if splitk is None and gn_stats and out_f32 and not out_nchw and Cout % 128 == 0 and Cout <= 512:
         partial = torch.empty(lib.sgam_tc_gn_partial_floats(B, Ho, Wo), device=x_hi.device)
+    written = ctypes.c_int(0)
     _lib.check(lib.sgam_conv2d_tc(x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), _ptr(bias),
                                   _ptr(residual), _ptr(y), _ptr(pair[0]), _ptr(pair[1]), B, H, W, Cin, Cout, ksize,
-                                  stride, int(out_nchw), nsplit, _ptr(partial), _ptr(splitk), _ptr(partial64), _stream()), "sgam_conv2d_tc")
-    if partial is not None:
+                                  stride, int(out_nchw), nsplit, _ptr(partial), _ptr(splitk), _ptr(partial64),
+                                  ctypes.byref(written), _stream()), "sgam_conv2d_tc")
+    # the library reports which statistics buffer it filled; attach exactly that one (never a guess)
+    if written.value == 1:
         y.gn_partial = partial          # GroupNorm statistics of y, fused into the epilogue (consumed by groupnorm_split)
-    if partial64 is not None:
+    elif written.value == 2:
         y.gn_partial64 = partial64      # ... or into the split-K reduction
     if out_f32 and out_split:
         return y, pair
