@@ -248,8 +248,15 @@ int sgam_gn_head_conv(const float *x, const float *gamma, const float *beta, flo
  * [B,T,T] matrix is never written.  q, k: [B,T,C] split bf16; vt = V^T [B,C,T] split bf16 (so that P.V is an A.B^T
  * product with K-major operands); o: [B,T,C] split bf16 (the proj_out conv's operand).  Needs C == 256, T % 256 == 0. */
 int sgam_attention_tc_supported(int B, int T, int C);
+/* Small batches do not have enough 256-query tiles to fill the SM pairs: the keys of a tile are then split kv_splits ways
+ * (flash-decoding style), every (tile, split) item leaves an un-normalised O and its (reference maximum, row sum) in the
+ * workspace and a merge kernel combines them.  sgam_attention_tc_splits gives the split count the library would choose
+ * (1 = no split, no workspace); the workspace holds sgam_attention_tc_workspace_bytes(B, T, kv_splits) bytes. */
+int sgam_attention_tc_splits(int B, int T);
+size_t sgam_attention_tc_workspace_bytes(int B, int T, int kv_splits);
 int sgam_attention_tc(const void *q_hi, const void *q_lo, const void *k_hi, const void *k_lo, const void *vt_hi,
-                      const void *vt_lo, void *o_hi, void *o_lo, int B, int T, int C, float scale, void *stream);
+                      const void *vt_lo, void *o_hi, void *o_lo, int B, int T, int C, float scale, int kv_splits,
+                      void *workspace, void *stream);
 
 /* Batched C = alpha * A . B^T (+ bias_m[row]) on tensor cores.  A [batch|1, M, K], B [batch|1, N, K] split-bf16
  * (a_batched / b_batched say whether the operand has the batch dimension); output fp32 C and/or split-bf16. */

@@ -57,9 +57,11 @@ constexpr float AT_TAU = 8.0f;                     // lazy-rescale threshold (lo
 static_assert(AT_SMEM <= 227 * 1024 - 512, "shared memory budget");
 
 struct AttnParams {
-    int T, tiles_per_img, total_tiles, n_iter;
+    int T, tiles_per_img, total_tiles, n_iter;     // total_tiles = work items = query tiles x key splits; n_iter = key tiles per item
+    int nsp;                                       // key splits per query tile (1 = the item sees every key and writes o itself)
     float c1;                                      // C^-0.5 * log2(e): exp(s * scale - m) = exp2(s * c1 - m * log2 e)
     __nv_bfloat16 *o_hi, *o_lo;                    // [B, T, 256]
+    float *o_part, *ml_part;                       // nsp > 1: un-normalised O [items][256][256] and (reference max, row sum) [items][256][2]
 };
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
@@ -168,9 +170,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ_hi, const __grid_consta
                 if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * AT_SLOT);
                 return ring + (size_t)s * AT_SLOT;
             };
-            for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++li) {
+            for (int item = cluster_id; item < p.total_tiles; item += num_clusters, ++li) {
+                const int tile = item / p.nsp, j0 = (item - tile * p.nsp) * n;      // this item's first key tile
                 const int b = tile / p.tiles_per_img, row0 = (tile - b * p.tiles_per_img) * 256 + (int)rank * 128;
-                auto load_k = [&](int j) {                     // keys [128 j + 64 rank, +64), channel block kb: {hi 8 KB | lo 8 KB}
+                auto load_k = [&](int jj) {                    // keys [128 j + 64 rank, +64), channel block kb: {hi 8 KB | lo 8 KB}
+                    const int j = j0 + jj;
                     for (int kb = 0; kb < AT_KB; ++kb) {
                         uint8_t *slot = acquire();
                         const uint32_t bar = map_to_cta(&full_bar[sc % AT_SLOTS], 0);
@@ -179,7 +183,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ_hi, const __grid_consta
                         ++sc;
                     }
                 };
-                auto load_v = [&](int j) {                     // V^T rows (channels) [128 rank, +128), keys [128 j + 64 kb, +64): hi slot, lo slot
+                auto load_v = [&](int jj) {                    // V^T rows (channels) [128 rank, +128), keys [128 j + 64 kb, +64): hi slot, lo slot
+                    const int j = j0 + jj;
                     for (int kb = 0; kb < AT_BN / 64; ++kb) {
                         uint8_t *slot = acquire();
                         tma2_load_3d(slot, &mapV_hi, map_to_cta(&full_bar[sc % AT_SLOTS], 0), j * AT_BN + kb * 64, (int)rank * 128, b);
@@ -210,7 +215,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ_hi, const __grid_consta
             constexpr uint32_t idesc_s = make_idesc(256, AT_BN), idesc_pv = make_idesc(256, AT_D);
             uint32_t sc = 0;                                   // slots consumed
             int g = 0, li = 0;                                 // key tiles issued before this query tile; query tiles done
-            for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++li) {
+            for (int item = cluster_id; item < p.total_tiles; item += num_clusters, ++li) {
                 auto issue_s = [&](int j) {                    // S(j) = Q . K_j^T into S[(g + j) & 1]
                     const uint32_t tmem_s = tmem_base + AT_S0 + (uint32_t)(((g + j) & 1) * AT_BN);
                     for (int kb = 0; kb < AT_KB; ++kb) {
@@ -276,7 +281,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ_hi, const __grid_consta
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const float c1 = p.c1;
         int g = 0, li = 0;
-        for (int tile = cluster_id; tile < p.total_tiles; tile += num_clusters, ++li) {
+        for (int item = cluster_id; item < p.total_tiles; item += num_clusters, ++li) {
+            const int tile = item / p.nsp;
             const int b = tile / p.tiles_per_img;
             const long long row = (long long)b * p.T + (long long)(tile - b * p.tiles_per_img) * 256 + (int)rank * 128 + q * 32 + lane;
             float m_used = 0.0f, l = 0.0f;                    // reference maximum (log2 domain) and row sum of exp2(s - m_used)
@@ -332,6 +338,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ_hi, const __grid_consta
             // ---- epilogue: O / l -> split bf16 [B, T, 256]; a thread writes 64 contiguous bytes per plane and chunk ----
             mbar_wait(&pv_done, (g + n - 1) & 1);
             tc_fence_after();
+            if (p.nsp > 1) {
+                // key-split item: un-normalised O and (m, l) to the workspace; attn_combine_kernel merges the splits
+                const long long prow = (long long)item * 256 + (int)rank * 128 + q * 32 + lane;
+                float *dp = p.o_part + prow * AT_D;
+#pragma unroll 1
+                for (int c = 0; c < AT_D; c += 32) {
+                    uint32_t o[32];
+                    tmem_ld32(t_o + (uint32_t)c, o);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4 *>(dp + c + i) = make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]), __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
+                }
+                *reinterpret_cast<float2 *>(p.ml_part + prow * 2) = make_float2(m_used, l);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(&o_free, 0));
+                g += n;
+                continue;
+            }
             const float inv = 1.0f / l;
             __nv_bfloat16 *dh = p.o_hi + row * AT_D, *dl = p.o_lo + row * AT_D;
 #pragma unroll 1
@@ -361,16 +386,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ_hi, const __grid_consta
     }
 }
 
+// Merge of the key splits (nsp > 1): o = sum_s 2^(m_s - M) O_s / sum_s 2^(m_s - M) l_s with M = max_s m_s, split to bf16 planes.
+// One warp per query row, 8 channels per lane; partial row of split s of query tile t: ((t * nsp + s) * 256 + row in tile).
+__global__ void __launch_bounds__(256)
+attn_combine_kernel(const float *__restrict__ o_part, const float *__restrict__ ml_part, int nsp, long long rows,
+                    __nv_bfloat16 *__restrict__ o_hi, __nv_bfloat16 *__restrict__ o_lo) {
+    SGAM_PDL_PROLOGUE();
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const long long tile = row >> 8, r = row & 255;
+    float M = -INFINITY;
+    for (int s = 0; s < nsp; ++s) M = fmaxf(M, __ldg(ml_part + ((tile * nsp + s) * 256 + r) * 2));
+    float L = 0.0f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < nsp; ++s) {
+        const long long pr = (tile * nsp + s) * 256 + r;
+        const float2 ml = __ldg(reinterpret_cast<const float2 *>(ml_part + pr * 2));
+        const float w = ex2_approx(ml.x - M);
+        L = fmaf(w, ml.y, L);
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(o_part + pr * AT_D) + 2 * lane), b4 = __ldg(reinterpret_cast<const float4 *>(o_part + pr * AT_D) + 2 * lane + 1);
+        acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+        acc[4] = fmaf(w, b4.x, acc[4]); acc[5] = fmaf(w, b4.y, acc[5]); acc[6] = fmaf(w, b4.z, acc[6]); acc[7] = fmaf(w, b4.w, acc[7]);
+    }
+    const float inv = 1.0f / L;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split2(acc[2 * k] * inv, acc[2 * k + 1] * inv, h[k], l[k]);
+    reinterpret_cast<uint4 *>(o_hi + row * AT_D)[lane] = make_uint4(h[0], h[1], h[2], h[3]);
+    reinterpret_cast<uint4 *>(o_lo + row * AT_D)[lane] = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 }  // namespace
 
 // 1 if the fused kernel handles this shape: 256 channels, a token count that tiles into 256-query pair tiles.
 extern "C" int sgam_attention_tc_supported(int B, int T, int C) { return B > 0 && C == AT_D && T >= 256 && T % 256 == 0; }
 
+// Key splits the fused kernel wants for this batch: 1 when the query tiles alone fill the SM pairs, otherwise the largest of
+// {2, 4, 8} that divides the key-tile count, leaves >= 2 key tiles per item and does not overshoot the machine.
+extern "C" int sgam_attention_tc_splits(int B, int T) {
+    const long long tiles = (long long)B * (T / 256);
+    const int n_iter = T / AT_BN, pairs = sm_count_cached() / 2;
+    if (tiles * 3 >= pairs * 2) return 1;
+    int best = 1;
+    for (int s = 2; s <= 8; s *= 2)
+        if (n_iter % s == 0 && n_iter / s >= 2 && tiles * s <= pairs + pairs / 4) best = s;
+    return best;
+}
+extern "C" size_t sgam_attention_tc_workspace_bytes(int B, int T, int kv_splits) {
+    return kv_splits > 1 ? (size_t)kv_splits * B * T * (AT_D + 2) * sizeof(float) : 0;
+}
+
 extern "C" int sgam_attention_tc(const void *q_hi, const void *q_lo, const void *k_hi, const void *k_lo, const void *vt_hi,
-                                 const void *vt_lo, void *o_hi, void *o_lo, int B, int T, int C, float scale, void *stream) {
+                                 const void *vt_lo, void *o_hi, void *o_lo, int B, int T, int C, float scale, int kv_splits,
+                                 void *workspace, void *stream) {
     SGAM_REQUIRE(q_hi && q_lo && k_hi && k_lo && vt_hi && vt_lo && o_hi && o_lo, "attention_tc: null pointer");
     SGAM_REQUIRE(sgam_attention_tc_supported(B, T, C), "attention_tc: needs C == 256 and T %% 256 == 0 (B=%d T=%d C=%d)", B, T, C);
     SGAM_REQUIRE(scale > 0.0f, "attention_tc: scale must be positive");
+    SGAM_REQUIRE(kv_splits >= 1 && (T / AT_BN) % kv_splits == 0 && (kv_splits == 1 || workspace), "attention_tc: kv_splits %d must divide the %d key tiles (and needs a workspace)", kv_splits, T / AT_BN);
     CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo;
     const long long qk_dims[3] = {C, T, B}, v_dims[3] = {T, C, B};
     const int q_box[3] = {64, 128, 1}, k_box[3] = {64, 64, 1}, v_box[3] = {64, 128, 1};
@@ -380,9 +452,11 @@ extern "C" int sgam_attention_tc(const void *q_hi, const void *q_lo, const void 
         (rc = make_map(&mv_hi, vt_hi, 3, v_dims, v_box)) || (rc = make_map(&mv_lo, vt_lo, 3, v_dims, v_box)))
         return rc;
     AttnParams p;
-    p.T = T; p.tiles_per_img = T / 256; p.total_tiles = B * (T / 256); p.n_iter = T / AT_BN;
+    p.T = T; p.tiles_per_img = T / 256; p.nsp = kv_splits; p.total_tiles = B * (T / 256) * kv_splits; p.n_iter = T / AT_BN / kv_splits;
     p.c1 = scale * 1.4426950408889634f;
     p.o_hi = (__nv_bfloat16 *)o_hi; p.o_lo = (__nv_bfloat16 *)o_lo;
+    p.o_part = (float *)workspace;
+    p.ml_part = p.o_part ? p.o_part + (size_t)kv_splits * B * T * AT_D : nullptr;
     static bool configured = false;
     if (!configured) {
         SGAM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
@@ -392,5 +466,10 @@ extern "C" int sgam_attention_tc(const void *q_hi, const void *q_lo, const void 
     const int clusters = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
     SGAM_PDL_LAUNCH(SGAM_PDL_GEMM2, attn_fwd_kernel, 2 * clusters, TC_THREADS, AT_SMEM, (cudaStream_t)stream, mq_hi, mq_lo, mk_hi, mk_lo, mv_hi,
                     mv_lo, p);
+    if (kv_splits > 1) {
+        const long long rows = (long long)B * T;
+        SGAM_PDL_LAUNCH(SGAM_PDL_MISC, attn_combine_kernel, (unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream, p.o_part, p.ml_part, kv_splits, rows,
+                        p.o_hi, p.o_lo);
+    }
     return SGAM_OK;
 }

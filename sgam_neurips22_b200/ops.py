@@ -484,19 +484,25 @@ def attention_tc_supported(B, T, C):
     return bool(_lib.load().sgam_attention_tc_supported(B, T, C))
 
 
-def attention_tc(q, k, vT, scale):
+def attention_tc(q, k, vT, scale, kv_splits=None):
     """Fused softmax(q . k^T * scale) . v on tcgen05 (AttnBlock, diffusionmodules/model.py:168-192): the [B,T,T] scores
-    never leave the SM.  q, k = (hi, lo) [B,T,C]; vT = (hi, lo) [B,C,T]; returns o = (hi, lo) [B,T,C]."""
+    never leave the SM.  q, k = (hi, lo) [B,T,C]; vT = (hi, lo) [B,C,T]; returns o = (hi, lo) [B,T,C].  kv_splits: key
+    splits per query tile (None = the library's choice: 1 unless the batch is too small to fill the SM pairs)."""
     lib = _lib.load()
     for n, t in (("q_hi", q[0]), ("q_lo", q[1]), ("k_hi", k[0]), ("k_lo", k[1]), ("vT_hi", vT[0]), ("vT_lo", vT[1])):
         _chk(t, torch.bfloat16, n)
     B, T, C = q[0].shape
     if tuple(k[0].shape) != (B, T, C) or tuple(vT[0].shape) != (B, C, T):
         raise RuntimeError(f"attention_tc: shapes q {tuple(q[0].shape)} k {tuple(k[0].shape)} vT {tuple(vT[0].shape)}")
+    if kv_splits is None:
+        kv_splits = lib.sgam_attention_tc_splits(B, T)
     o = _bf16_pair((B, T, C), q[0].device)
+    ws = None
+    if kv_splits > 1:
+        ws = torch.empty(lib.sgam_attention_tc_workspace_bytes(B, T, kv_splits) // 4, device=q[0].device)
     _lib.check(lib.sgam_attention_tc(q[0].data_ptr(), q[1].data_ptr(), k[0].data_ptr(), k[1].data_ptr(), vT[0].data_ptr(),
-                                     vT[1].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), B, T, C, float(scale), _stream()),
-               "sgam_attention_tc")
+                                     vT[1].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), B, T, C, float(scale), int(kv_splits),
+                                     _ptr(ws), _stream()), "sgam_attention_tc")
     return o
 
 

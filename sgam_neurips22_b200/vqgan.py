@@ -157,14 +157,12 @@ class VQGANEngine:
         return self.conv(f"{name}.proj_out", o, ksize=1, residual=x)
 
     def use_fused_attention(self, B, T, C):
-        """The fused kernel works on 256-query pair tiles, one per cluster: it needs enough of them to fill the machine
-        (at one trajectory a 4096-token block is 16 tiles on 74 SM pairs -- there the three-pass path, which spreads
-        the score matrix over every SM, is faster).  SGAM_ATTN=fused|3pass overrides the choice (tests, experiments)."""
+        """256-channel blocks whose token count tiles into 256-query pair tiles run the fused kernel at every batch size
+        (small batches split the keys of a tile over several SM pairs and merge); SGAM_ATTN=3pass selects the three-pass
+        path (QK^T GEMM -> softmax -> PV GEMM), which the 512-channel mid blocks always take."""
         import os
         mode = os.environ.get("SGAM_ATTN", "auto")
-        if mode == "3pass" or self.nsplit != 3 or not ops.attention_tc_supported(B, T, C):
-            return False
-        return mode == "fused" or B * (T // 256) >= 48
+        return mode != "3pass" and self.nsplit == 3 and ops.attention_tc_supported(B, T, C)
 
     # ------------------------------------------------------------------ encoder / decoder
     def encoder(self, h):

@@ -29,10 +29,10 @@ def reference(q, k, v, scale):
     return torch.einsum("bts,bsc->btc", torch.softmax(s, dim=-1), v.double())
 
 
-def run(ops, q, k, v, scale):
+def run(ops, q, k, v, scale, kv_splits=None):
     qs, ks = ops.split_weight(q), ops.split_weight(k)
     vts = ops.split_weight(v.transpose(1, 2).contiguous())
-    oh, ol = ops.attention_tc(qs, ks, vts, scale)
+    oh, ol = ops.attention_tc(qs, ks, vts, scale, kv_splits=kv_splits)
     torch.cuda.synchronize()
     return oh.float() + ol.float()
 
@@ -57,6 +57,27 @@ def test_fused_attention_matches_float64(ops, B, T):
     row_err = ((out.double() - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item()
     assert row_err < 5e-4, row_err
     assert torch.equal(out, run(ops, q, k, v, scale)), "fused attention must be deterministic"
+
+
+@pytest.mark.parametrize("B,T,splits", [(1, 4096, 4), (2, 4096, 2), (1, 1024, 4), (3, 2048, 8), (1, 4096, 1)])
+def test_key_split_items_merge_to_the_same_attention(ops, B, T, splits):
+    """Small batches: the keys of a query tile are split over several SM pairs and merged (un-normalised O, reference
+    maximum and row sum per split).  Same bar as the unsplit kernel; the library's own choice is covered as well."""
+    from sgam_neurips22_b200 import _lib
+    C = 256
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + T + splits)
+    q = torch.randn(B, T, C, generator=g, device="cuda") * 1.5
+    k = torch.randn(B, T, C, generator=g, device="cuda")
+    k = k * torch.linspace(0.3, 3.0, T, device="cuda")[None, :, None]          # later splits hold the larger scores
+    v = torch.randn(B, T, C, generator=g, device="cuda")
+    scale = C ** -0.5
+    ref = reference(q, k, v, scale)
+    out = run(ops, q, k, v, scale, kv_splits=splits)
+    assert rel(out, ref) < 5e-5
+    assert ((out.double() - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item() < 5e-4
+    auto = _lib.load().sgam_attention_tc_splits(B, T)
+    assert auto >= 1 and (T // 128) % auto == 0
+    assert rel(run(ops, q, k, v, scale), ref) < 5e-5
 
 
 def test_fused_attention_growing_maxima_exercise_the_o_correction(ops):
