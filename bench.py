@@ -251,49 +251,6 @@ class StepHarness:
         self.pin_depth.copy_(depth, non_blocking=True)
         torch.cuda.current_stream().synchronize()                      # the caller reads the frame before the next step
 
-    def e2e_pipelined_run(self, steps):
-        """The same public-API step, double-buffered over two CUDA streams: step i+1's host->device copies and its splat
-        (VQModel.get_x) run on a second stream while step i's network runs on the first; the host waits for step i-1's
-        frame (device->host copy into pinned memory) before it issues step i+1.  Every step's H2D and D2H are inside the
-        timed region; only their overlap with the neighbouring step's compute differs from `e2e`."""
-        main = torch.cuda.current_stream()
-        side = getattr(self, "_side", None) or torch.cuda.Stream()
-        self._side = side
-        bufs = [(torch.empty_like(self.pin_rgb).pin_memory(), torch.empty_like(self.pin_depth).pin_memory()) for _ in range(2)]
-        outs = [(torch.empty_like(self.out_rgb), torch.empty_like(self.out_depth)) for _ in range(2)]
-        done = [None, None]
-
-        def stage_inputs():
-            side.wait_stream(main)                 # allocator hygiene: buffers freed on main are safe to reuse on side
-            with torch.cuda.stream(side):
-                x, _, mask, _ = self.model.get_x(dict(self.api_batch), self.ds, return_extrapolation_mask=True, no_depth_range=True, parallel=True)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            return x, mask, ev
-
-        nxt = stage_inputs()
-        for i in range(steps):
-            x, mask, ev = nxt
-            main.wait_event(ev)
-            x.record_stream(main); mask.record_stream(main)
-            if i + 1 < steps:
-                nxt = stage_inputs()               # overlaps the network of step i
-            decs, _, pre, quants = self.model(x, topk=1, extrapolation_mask=mask, get_pre_quantized_feature=True,
-                                              get_quantized_feature=True, sample_number=1)
-            o_rgb, o_depth = outs[i & 1]
-            rgb, depth = self.ops.frame_outputs(decs[0][0], self.ds, rgb_u8=o_rgb, depth=o_depth)
-            p_rgb, p_depth = bufs[i & 1]
-            p_rgb.copy_(rgb, non_blocking=True)
-            p_depth.copy_(depth, non_blocking=True)
-            e = torch.cuda.Event()
-            e.record(main)
-            done[i & 1] = e
-            if done[(i + 1) & 1] is not None:
-                done[(i + 1) & 1].synchronize()    # the caller consumes frame i-1 while frame i is in flight
-        for e in done:
-            if e is not None:
-                e.synchronize()
-
     def digest(self):
         """SHA-256 of the step's outputs (uint8 RGB + fp32 depth bytes) after one resident run."""
         self.run()
@@ -576,11 +533,8 @@ def main():
     for _ in range(args.warmup):
         h.e2e()
     e2e_steps = max(3, min(args.steps, 20))
-    ms_e2e_serial = time_steps(h.e2e, e2e_steps, world)
-    h.e2e_pipelined_run(3)
-    ms_e2e = time_steps(lambda: h.e2e_pipelined_run(e2e_steps), 1, world)
+    ms_e2e = time_steps(h.e2e, e2e_steps, world)
     e2e_value = B * world * e2e_steps / (ms_e2e / 1000.0)
-    e2e_serial_value = B * world * e2e_steps / (ms_e2e_serial / 1000.0)
     roof = h.roofline(peaks, ms / args.steps, dump=args.dump_gemm if rank == 0 else None)
     traffic, traffic_src = latest_traffic() if (ds == "clevr-infinite" and B == 8 and res == 256) else (None, None)
     roof["traffic"], roof["traffic_source"] = traffic, traffic_src
@@ -778,12 +732,7 @@ def main():
             "dtype": "f32 (tensor-core products as 3-term split bf16, fp32 accumulate)", "data": "synthetic", "config": cfg,
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h.h2d), "d2h_bytes_per_step": int(h.d2h),
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "VQModel.get_x + VQModel.forward(topk=1) + frame_outputs from / to pinned host buffers, double-buffered over two "
-                           "CUDA streams (step i+1's H2D + splat overlap step i's network; the host waits for frame i-1 before issuing "
-                           "step i+1); every step's H2D and D2H are inside the timed region",
-                    "serial": {"value": e2e_serial_value, "ms_per_step": ms_e2e_serial / e2e_steps,
-                               "note": "the same calls strictly one step at a time (upload, compute, read back, synchronise)"}},
+                    "ms_per_step": ms_e2e / e2e_steps, "api": "VQModel.get_x + VQModel.forward(topk=1) + frame_outputs, pinned host buffers"},
             "gpu_launches": h.launches_per_step * args.steps, "gpu_launches_per_step": h.launches_per_step,
             "roofline": roof,
             "kernels": {
