@@ -40,10 +40,7 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
                       __nv_bfloat16 *__restrict__ lo, long long HW, int C, int S, int swish) {
     SGAM_PDL_PROLOGUE();
     __shared__ float mean_s[32], rstd_s[32];
-    // Reverse traversal (last image first, each image back to front): the producing GEMM wrote the tensor front to back,
-    // so its tail is what still sits in the 126 MB L2 when this kernel starts, and the consuming GEMM starts at the front,
-    // which this kernel then writes last.
-    const int b = gridDim.y - 1 - blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     if (meanrstd && S > 0) {            // per-pixel-block sums from the producing conv's epilogue, S = blocks per image (<= 64)
         gn_mean_rstd_from_tiles(meanrstd, b, S, (double)HW * (C / 32), mean_s, rstd_s);
     } else if (meanrstd) {              // statistics already finalised by gn_finalize_kernel
@@ -62,13 +59,13 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
         float4 v0[4], v1[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const long long er = e0 + u * stride, e = total - 1 - er;
-            if (er < total) { v0[u] = __ldg(src + 2 * e); v1[u] = __ldg(src + 2 * e + 1); }
+            const long long e = e0 + u * stride;
+            if (e < total) { v0[u] = __ldg(src + 2 * e); v1[u] = __ldg(src + 2 * e + 1); }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const long long er = e0 + u * stride, e = total - 1 - er;
-            if (er >= total) break;
+            const long long e = e0 + u * stride;
+            if (e >= total) break;
             const int c = (int)(e % CO) * 8, g0 = c / cpg, g1 = (c + 4) / cpg;
             const float mu0 = mean_s[g0], rs0 = rstd_s[g0], mu1 = mean_s[g1], rs1 = rstd_s[g1];
             const float4 ga0 = __ldg(reinterpret_cast<const float4 *>(gamma + c)), ga1 = __ldg(reinterpret_cast<const float4 *>(gamma + c + 4));
