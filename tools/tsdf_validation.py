@@ -45,12 +45,22 @@ def run(ds, seed_index):
     T0 = np.eye(4); T0[:3, :3], T0[:3, 3] = node["R"], node["t"]
     pipe.volume.integrate(depth.contiguous(), rgb, pipe.K, T0, depth_trunc=20.0)
     vox = pipe.volume.voxel_length
+
+    def timed(fn, n=10):                                   # CUDA-event time of a call on REAL data, after one warm-up
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
     H, W = pipe.image_resolution
     out = {"dataset": ds, "seed_index": seed_index, "voxel_length": vox, "sdf_trunc": pipe.volume.sdf_trunc,
            "seed_depth_range": [float(depth.min()), float(depth.max())],
            "units_in_use": pipe.volume.units_in_use(), "volume_bytes": pipe.volume.memory_bytes(), "dropped_units": pipe.volume.dropped_units()}
     d0 = pipe.volume.render_depth(pipe.K, T0, H, W, z_far=pipe._z_far).cpu().numpy()
     out["self_view_vs_seed_depth"] = stats(d0, depth.cpu().numpy(), vox)
+    out["raycast_ms_real_seed_frame"] = timed(lambda: pipe.volume.render_depth(pipe.K, T0, H, W, z_far=pipe._z_far))
     # the splat path sees the seed depth the frame store holds (for CLEVR: after the second ray->z conversion, :582-590);
     # compare like with like: splat the depth that was integrated
     pipe._frames[first] = (rgb, depth)
@@ -62,6 +72,8 @@ def run(ds, seed_index):
         d_s = forward_splat_depth(pipe, [node], T).cpu().numpy()
         views[f"pose{k}_{c[0]}_{c[1]}"] = stats(d_t, d_s, vox)
     out["novel_views_vs_forward_splat"] = views
+    # re-integration of the same real frame (the reference fuses a selected source at every step): time of touch + integrate
+    out["integrate_ms_real_seed_frame"] = timed(lambda: pipe.volume.integrate(depth.contiguous(), rgb, pipe.K, T0, depth_trunc=20.0), n=5)
     return out
 
 
@@ -74,4 +86,5 @@ if __name__ == "__main__":
         nv = list(r["novel_views_vs_forward_splat"].values())
         print(r["dataset"], r["seed_index"], "self: median %.4f m (%.2f vox) p90 %.4f" % (sv["median_m"], sv["median_voxels"], sv["p90_m"]),
               "| novel: " + ", ".join("median %.4f m (%.2f vox) p90 %.4f cov %.2f/%.2f" % (v["median_m"], v["median_voxels"], v["p90_m"], v["coverage_tsdf"], v["coverage_ref"]) for v in nv),
-              "| units", r["units_in_use"], "bytes %.2f GB" % (r["volume_bytes"] / 2**30))
+              "| units", r["units_in_use"], "bytes %.2f GB" % (r["volume_bytes"] / 2**30),
+              "| raycast %.3f ms integrate %.3f ms" % (r["raycast_ms_real_seed_frame"], r["integrate_ms_real_seed_frame"]))
