@@ -201,7 +201,6 @@ int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const v
  * which kernel it chose.  defer_reduce != 0: when the K loop is split, only the GEMM is launched; y is NOT written,
  * the partial tensors stay in splitk_ws and *host_stats_written = 3 | (ksplit << 8): the caller finishes with
  * sgam_splitk_finish, fused with the first thing the consumer does (GroupNorm + swish + split, or a plain split). */
-int sgam_splitk_finish_fused_ok(int B, long long HW, int C);      /* does the one-launch finish pay for this shape? */
 int sgam_splitk_finish(const float *ws, int ksplit, const float *bias, const float *residual, float *y, const float *gamma,
                        const float *beta, void *hi, void *lo, int B, long long HW, int C, int mode, int swish, void *stream);
 

@@ -50,7 +50,6 @@ SIGNATURES = {
     "sgam_tc_supported_conv": (c_i, [c_i, c_i, c_i, c_i, c_i, c_i]),
     "sgam_conv2d_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p,
                              ctypes.POINTER(c_i), c_i, c_p]),
-    "sgam_splitk_finish_fused_ok": (c_i, [c_i, c_ll, c_i]),
     "sgam_splitk_finish": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_i, c_p]),
     "sgam_groupnorm_split_apply": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p]),
     "sgam_conv2d_tc_splitk_floats": (c_ll, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),

@@ -461,60 +461,37 @@ __device__ __forceinline__ double fin_ld_remote_f64(const double *local, uint32_
     return v;
 }
 
-constexpr int FIN_T = 512;                                      // threads per CTA
-constexpr int FIN_U = 4;                                        // independent float4 groups per thread and round (loads batched)
-
-__global__ void __launch_bounds__(FIN_T)
+__global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float *__restrict__ ws, long long split_stride, int ksplit, const float *__restrict__ bias,
                      const float *__restrict__ R, float *__restrict__ y, const float *__restrict__ gamma, const float *__restrict__ beta,
                      __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, long long HW, int C, int mode, int swish) {
     SGAM_PDL_PROLOGUE();
-    __shared__ double red[FIN_T][2];
+    __shared__ double red[256][2];
     __shared__ double part_s[32][2];
-    __shared__ double gath[16][32][2];
     __shared__ float mean_s[32], rstd_s[32];
     const uint32_t rank = fin_cluster_rank(), CL = fin_cluster_size();
     const int b = blockIdx.x / CL, tid = threadIdx.x;
-    const int CQ = C / 4, PL = FIN_T / CQ, cq = tid % CQ, pl = tid / CQ, cpg = C / 32;
+    const int CQ = C / 4, PL = 256 / CQ, cq = tid % CQ, pl = tid / CQ, cpg = C / 32;
     const long long chunk = HW / CL, pbeg = rank * chunk, pend = pbeg + chunk;
     const long long base = (long long)b * HW * CQ + cq;
-    const float4 bv = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
     float sum = 0.f, sq = 0.f;
-    // phase 1: y = sum of the partials in split order (+ bias) (+ residual) -- the arithmetic of splitk_reduce_stats_kernel --
-    // FIN_U pixels per round with every load of the round in flight before the first add
-    for (long long p0 = pbeg + pl; p0 < pend; p0 += (long long)FIN_U * PL) {
-        float4 a[FIN_U], r[FIN_U];
-#pragma unroll
-        for (int u = 0; u < FIN_U; ++u) {
-            const long long p = p0 + (long long)u * PL;
-            if (p < pend) {
-                a[u] = __ldg(reinterpret_cast<const float4 *>(ws) + base + p * CQ);
-                if (R) r[u] = __ldg(reinterpret_cast<const float4 *>(R) + base + p * CQ);
+    if (pl < PL) {
+        const float4 bv = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long p = pbeg + pl; p < pend; p += PL) {
+            const long long e = base + p * CQ;
+            float4 a = __ldg(reinterpret_cast<const float4 *>(ws) + e);
+            for (int k = 1; k < ksplit; ++k) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (long long)k * split_stride) + e);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
             }
-        }
-        for (int k = 1; k < ksplit; ++k) {
-            float4 v[FIN_U];
-#pragma unroll
-            for (int u = 0; u < FIN_U; ++u) {
-                const long long p = p0 + (long long)u * PL;
-                if (p < pend) v[u] = __ldg(reinterpret_cast<const float4 *>(ws + (long long)k * split_stride) + base + p * CQ);
+            if (bias) { a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w; }
+            if (R) {
+                const float4 r = __ldg(reinterpret_cast<const float4 *>(R) + e);
+                a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
             }
-#pragma unroll
-            for (int u = 0; u < FIN_U; ++u) {
-                const long long p = p0 + (long long)u * PL;
-                if (p < pend) { a[u].x += v[u].x; a[u].y += v[u].y; a[u].z += v[u].z; a[u].w += v[u].w; }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < FIN_U; ++u) {
-            const long long p = p0 + (long long)u * PL;
-            if (p >= pend) break;
-            float4 t = a[u];
-            if (bias) { t.x += bv.x; t.y += bv.y; t.z += bv.z; t.w += bv.w; }
-            if (R) { t.x += r[u].x; t.y += r[u].y; t.z += r[u].z; t.w += r[u].w; }
-            reinterpret_cast<float4 *>(y)[base + p * CQ] = t;
-            sum += (t.x + t.y) + (t.z + t.w);
-            sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
+            reinterpret_cast<float4 *>(y)[e] = a;
+            sum += (a.x + a.y) + (a.z + a.w);
+            sq = fmaf(a.x, a.x, sq); sq = fmaf(a.y, a.y, sq); sq = fmaf(a.z, a.z, sq); sq = fmaf(a.w, a.w, sq);
         }
     }
     if (mode == 0) return;                                      // uniform over the whole grid
@@ -529,15 +506,9 @@ splitk_finish_kernel(const float *__restrict__ ws, long long split_stride, int k
             part_s[tid][0] = a; part_s[tid][1] = q;
         }
         fin_cluster_sync();                                      // every CTA's group sums are in its shared memory
-        if (tid < 32 * (int)CL) {                                // all (rank, group) pairs fetched in parallel through DSMEM ...
-            const int g = tid & 31, r = tid >> 5;
-            gath[r][g][0] = fin_ld_remote_f64(&part_s[g][0], (uint32_t)r);
-            gath[r][g][1] = fin_ld_remote_f64(&part_s[g][1], (uint32_t)r);
-        }
-        __syncthreads();
-        if (tid < 32) {                                          // ... and added in rank order (deterministic)
+        if (tid < 32) {
             double a = 0.0, q = 0.0;
-            for (uint32_t r = 0; r < CL; ++r) { a += gath[r][tid][0]; q += gath[r][tid][1]; }
+            for (uint32_t r = 0; r < CL; ++r) { a += fin_ld_remote_f64(&part_s[tid][0], r); q += fin_ld_remote_f64(&part_s[tid][1], r); }
             const double n = (double)HW * cpg, mean = a / n;
             double var = q / n - mean * mean;
             var = var < 0.0 ? 0.0 : var;
@@ -547,6 +518,7 @@ splitk_finish_kernel(const float *__restrict__ ws, long long split_stride, int k
         fin_cluster_sync();                                      // nobody leaves (or overwrites part_s) while a peer still reads it
     }
     __syncthreads();
+    if (pl >= PL) return;
     const int g = (cq * 4) / cpg;
     float mu = 0.f, rs = 1.f;
     float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -554,31 +526,22 @@ splitk_finish_kernel(const float *__restrict__ ws, long long split_stride, int k
         mu = mean_s[g]; rs = rstd_s[g];
         ga = __ldg(reinterpret_cast<const float4 *>(gamma) + cq); be = __ldg(reinterpret_cast<const float4 *>(beta) + cq);
     }
-    for (long long p0 = pbeg + pl; p0 < pend; p0 += (long long)FIN_U * PL) {
-        float4 a[FIN_U];
+    for (long long p = pbeg + pl; p < pend; p += PL) {
+        const long long e = base + p * CQ;
+        float4 a = reinterpret_cast<const float4 *>(y)[e];        // this thread wrote it in phase 1
+        float o[4] = {a.x, a.y, a.z, a.w};
+        if (mode == 2) {
+            o[0] = (a.x - mu) * rs * ga.x + be.x; o[1] = (a.y - mu) * rs * ga.y + be.y;
+            o[2] = (a.z - mu) * rs * ga.z + be.z; o[3] = (a.w - mu) * rs * ga.w + be.w;
+            if (swish) {
 #pragma unroll
-        for (int u = 0; u < FIN_U; ++u) {
-            const long long p = p0 + (long long)u * PL;
-            if (p < pend) a[u] = reinterpret_cast<const float4 *>(y)[base + p * CQ];          // this thread wrote it in phase 1
-        }
-#pragma unroll
-        for (int u = 0; u < FIN_U; ++u) {
-            const long long p = p0 + (long long)u * PL;
-            if (p >= pend) break;
-            float o[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
-            if (mode == 2) {
-                o[0] = (a[u].x - mu) * rs * ga.x + be.x; o[1] = (a[u].y - mu) * rs * ga.y + be.y;
-                o[2] = (a[u].z - mu) * rs * ga.z + be.z; o[3] = (a[u].w - mu) * rs * ga.w + be.w;
-                if (swish) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) o[k] = __fdividef(o[k], 1.0f + __expf(-o[k]));
-                }
+                for (int k = 0; k < 4; ++k) o[k] = __fdividef(o[k], 1.0f + __expf(-o[k]));
             }
-            uint32_t h0, l0, h1, l1;
-            split2(o[0], o[1], h0, l0); split2(o[2], o[3], h1, l1);
-            reinterpret_cast<uint2 *>(hi)[base + p * CQ] = make_uint2(h0, h1);
-            reinterpret_cast<uint2 *>(lo)[base + p * CQ] = make_uint2(l0, l1);
         }
+        uint32_t h0, l0, h1, l1;
+        split2(o[0], o[1], h0, l0); split2(o[2], o[3], h1, l1);
+        reinterpret_cast<uint2 *>(hi)[e] = make_uint2(h0, h1);
+        reinterpret_cast<uint2 *>(lo)[e] = make_uint2(l0, l1);
     }
 }
 
@@ -716,13 +679,6 @@ extern "C" int sgam_stem_conv_in(const float *x, const uint8_t *mask, const floa
 // Finish of a deferred split-K convolution (sgam_conv2d_tc with defer_reduce): y = sum of the ksplit partials (+ bias)
 // (+ residual), and in the same launch the consumer's operand: mode 2 = GroupNorm(32, C, eps 1e-6) (+ swish) -> split bf16,
 // mode 1 = plain split bf16, mode 0 = y only.  ws [ksplit][B*HW*C]; C in {128, 256, 512, 1024}.
-// sgam_splitk_finish_fused_ok: whether the one-launch finish pays: a cluster of 16 CTAs per image must cover the tensor in a
-// few rounds (measured: beyond ~64 K float4 per image the two wide launches of the plain path are faster).
-extern "C" int sgam_splitk_finish_fused_ok(int B, long long HW, int C) {
-    if (!(C == 128 || C == 256 || C == 512 || C == 1024) || B <= 0 || HW <= 0) return 0;
-    return HW * (C / 4) <= 65536;
-}
-
 extern "C" int sgam_splitk_finish(const float *ws, int ksplit, const float *bias, const float *residual, float *y, const float *gamma,
                                   const float *beta, void *hi, void *lo, int B, long long HW, int C, int mode, int swish, void *stream) {
     SGAM_REQUIRE(ws && y && ksplit >= 1 && B > 0 && HW > 0, "splitk_finish: bad arguments");
@@ -737,7 +693,7 @@ extern "C" int sgam_splitk_finish(const float *ws, int ksplit, const float *bias
     int CL = 16;                                              // CTAs per image: the largest power of two <= 16 that divides HW
     while (CL > 1 && (HW % CL != 0)) CL >>= 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(B * CL)); cfg.blockDim = dim3(FIN_T); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cfg.gridDim = dim3((unsigned)(B * CL)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

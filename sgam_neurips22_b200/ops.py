@@ -440,7 +440,7 @@ def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=
     if residual is not None:
         _chk(materialize(residual), name="residual")
     partial = splitk = partial64 = None
-    defer = bool(defer) and bool(lib.sgam_splitk_finish_fused_ok(B, Ho * Wo, Cout))
+    defer = bool(defer) and Cout in (128, 256, 512, 1024)
     if out_f32 and not out_split and not out_nchw and Cout % 32 == 0:
         n_ws = lib.sgam_conv2d_tc_splitk_floats(B, H, W, Cin, Cout, ksize, stride)
         if n_ws > 0:                    # under-filled grid: split the K loop; the reduce kernel also takes the statistics
