@@ -195,14 +195,10 @@ int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize, int strid
 int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                    const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
                    int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws,
-                   double *splitk_gn_partial, int *host_stats_written, int defer_reduce, void *stream);
+                   double *splitk_gn_partial, int *host_stats_written, void *stream);
 /* host_stats_written (HOST pointer or NULL) receives which GroupNorm statistics the call produced: 0 none, 1 the fp32
  * per-pixel-block sums in gn_partial, 2 the fp64 split sums in splitk_gn_partial -- the library, not the caller, knows
- * which kernel it chose.  defer_reduce != 0: when the K loop is split, only the GEMM is launched; y is NOT written,
- * the partial tensors stay in splitk_ws and *host_stats_written = 3 | (ksplit << 8): the caller finishes with
- * sgam_splitk_finish, fused with the first thing the consumer does (GroupNorm + swish + split, or a plain split). */
-int sgam_splitk_finish(const float *ws, int ksplit, const float *bias, const float *residual, float *y, const float *gamma,
-                       const float *beta, void *hi, void *lo, int B, long long HW, int C, int mode, int swish, void *stream);
+ * which kernel it chose. */
 
 /* Upsample = nearest x2 + 3x3 conv (diffusionmodules/model.py:49-52) in sub-pixel form: each output parity (py, px) is a
  * 2x2 convolution of the LOW-resolution operand with pre-summed taps.  x_hi/x_lo [B,H,W,Cin] (low resolution);

@@ -49,8 +49,7 @@ SIGNATURES = {
     "sgam_softmax_split": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_p]),
     "sgam_tc_supported_conv": (c_i, [c_i, c_i, c_i, c_i, c_i, c_i]),
     "sgam_conv2d_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p,
-                             ctypes.POINTER(c_i), c_i, c_p]),
-    "sgam_splitk_finish": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_i, c_p]),
+                             ctypes.POINTER(c_i), c_p]),
     "sgam_groupnorm_split_apply": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_ll, c_i, c_i, c_p]),
     "sgam_conv2d_tc_splitk_floats": (c_ll, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
     "sgam_tc_gn_partial_floats": (c_ll, [c_i, c_i, c_i]),

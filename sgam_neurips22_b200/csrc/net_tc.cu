@@ -364,7 +364,7 @@ extern "C" int sgam_tc_supported_conv(int H, int W, int Cin, int Cout, int ksize
 extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias,
                               const float *residual, float *y, void *y_hi, void *y_lo, int B, int H, int W, int Cin, int Cout,
                               int ksize, int stride, int out_nchw, int nsplit, float *gn_partial, float *splitk_ws,
-                              double *splitk_gn_partial, int *host_stats_written, int defer_reduce, void *stream) {
+                              double *splitk_gn_partial, int *host_stats_written, void *stream) {
     SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && (y || (y_hi && y_lo)), "conv2d_tc: null pointer");
     // which GroupNorm statistics this call produces (the caller must not guess the kernel choice): 0 none, 1 the fp32
     // per-pixel-block sums in gn_partial (every unsplit path), 2 the fp64 sums in splitk_gn_partial (split-K + reduce)
@@ -435,10 +435,6 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
         p.splitk_ws = splitk_ws; p.split_stride = (long long)B * Ho * Wo * Cout;
         int rc2 = launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, (cudaStream_t)stream);
         if (rc2) return rc2;
-        if (defer_reduce && host_stats_written) {             // the caller finishes with sgam_splitk_finish (fused with its consumer)
-            stats_written = 3 | (p.ksplit << 8);
-            return SGAM_OK;
-        }
         const long long total_q = p.split_stride / 4;
         if (splitk_gn_partial && Cout % 128 == 0 && Cout <= 1024) {          // reduction + GroupNorm statistics in one pass
             stats_written = 2;

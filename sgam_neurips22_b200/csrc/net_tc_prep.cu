@@ -438,113 +438,6 @@ stem_conv_in_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mas
     }
 }
 
-
-// ------------------------------------------------------------------------------------------------ split-K finish
-// Finish of a split-K convolution fused with what its consumer does first.  The split-K GEMM leaves ksplit raw partial
-// tensors in a workspace; round 1 then ran splitk_reduce_stats_kernel (sum + bias + residual -> y, GroupNorm partial sums)
-// and, as the consumer's first step, gn_apply_split_kernel (or split_bf16_kernel): two tiny latency-bound launches per
-// layer -- 48 + ~60 of the 277 launches of a single-trajectory frame.  Here ONE launch does both: a cluster of up to 16
-// CTAs owns one image; phase 1 sums the partials in split order (bit-identical to the reduce kernel), writes y and
-// accumulates per-group sums; the CTAs exchange their fp64 group sums through distributed shared memory (fixed rank order:
-// deterministic) and phase 2 normalises (+ swish), splits to bf16 planes and writes the consumer's operand.  mode 1: no
-// normalisation (plain split for a following conv); mode 0: y only.
-__device__ __forceinline__ uint32_t fin_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t fin_cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void fin_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ double fin_ld_remote_f64(const double *local, uint32_t rank) {
-    uint32_t addr;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(addr) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
-    double v;
-    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(256)
-splitk_finish_kernel(const float *__restrict__ ws, long long split_stride, int ksplit, const float *__restrict__ bias,
-                     const float *__restrict__ R, float *__restrict__ y, const float *__restrict__ gamma, const float *__restrict__ beta,
-                     __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, long long HW, int C, int mode, int swish) {
-    SGAM_PDL_PROLOGUE();
-    __shared__ double red[256][2];
-    __shared__ double part_s[32][2];
-    __shared__ float mean_s[32], rstd_s[32];
-    const uint32_t rank = fin_cluster_rank(), CL = fin_cluster_size();
-    const int b = blockIdx.x / CL, tid = threadIdx.x;
-    const int CQ = C / 4, PL = 256 / CQ, cq = tid % CQ, pl = tid / CQ, cpg = C / 32;
-    const long long chunk = HW / CL, pbeg = rank * chunk, pend = pbeg + chunk;
-    const long long base = (long long)b * HW * CQ + cq;
-    float sum = 0.f, sq = 0.f;
-    if (pl < PL) {
-        const float4 bv = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long p = pbeg + pl; p < pend; p += PL) {
-            const long long e = base + p * CQ;
-            float4 a = __ldg(reinterpret_cast<const float4 *>(ws) + e);
-            for (int k = 1; k < ksplit; ++k) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(ws + (long long)k * split_stride) + e);
-                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-            }
-            if (bias) { a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w; }
-            if (R) {
-                const float4 r = __ldg(reinterpret_cast<const float4 *>(R) + e);
-                a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-            }
-            reinterpret_cast<float4 *>(y)[e] = a;
-            sum += (a.x + a.y) + (a.z + a.w);
-            sq = fmaf(a.x, a.x, sq); sq = fmaf(a.y, a.y, sq); sq = fmaf(a.z, a.z, sq); sq = fmaf(a.w, a.w, sq);
-        }
-    }
-    if (mode == 0) return;                                      // uniform over the whole grid
-    if (mode == 2) {
-        red[tid][0] = (double)sum; red[tid][1] = (double)sq;
-        __syncthreads();
-        if (tid < 32) {                                          // fixed-order group reduction inside the CTA
-            const int nq = CQ / 32;
-            double a = 0.0, q = 0.0;
-            for (int l = 0; l < PL; ++l)
-                for (int k = 0; k < nq; ++k) { const int t = l * CQ + tid * nq + k; a += red[t][0]; q += red[t][1]; }
-            part_s[tid][0] = a; part_s[tid][1] = q;
-        }
-        fin_cluster_sync();                                      // every CTA's group sums are in its shared memory
-        if (tid < 32) {
-            double a = 0.0, q = 0.0;
-            for (uint32_t r = 0; r < CL; ++r) { a += fin_ld_remote_f64(&part_s[tid][0], r); q += fin_ld_remote_f64(&part_s[tid][1], r); }
-            const double n = (double)HW * cpg, mean = a / n;
-            double var = q / n - mean * mean;
-            var = var < 0.0 ? 0.0 : var;
-            mean_s[tid] = (float)mean;
-            rstd_s[tid] = (float)(1.0 / sqrt(var + 1e-6));
-        }
-        fin_cluster_sync();                                      // nobody leaves (or overwrites part_s) while a peer still reads it
-    }
-    __syncthreads();
-    if (pl >= PL) return;
-    const int g = (cq * 4) / cpg;
-    float mu = 0.f, rs = 1.f;
-    float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mode == 2) {
-        mu = mean_s[g]; rs = rstd_s[g];
-        ga = __ldg(reinterpret_cast<const float4 *>(gamma) + cq); be = __ldg(reinterpret_cast<const float4 *>(beta) + cq);
-    }
-    for (long long p = pbeg + pl; p < pend; p += PL) {
-        const long long e = base + p * CQ;
-        float4 a = reinterpret_cast<const float4 *>(y)[e];        // this thread wrote it in phase 1
-        float o[4] = {a.x, a.y, a.z, a.w};
-        if (mode == 2) {
-            o[0] = (a.x - mu) * rs * ga.x + be.x; o[1] = (a.y - mu) * rs * ga.y + be.y;
-            o[2] = (a.z - mu) * rs * ga.z + be.z; o[3] = (a.w - mu) * rs * ga.w + be.w;
-            if (swish) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) o[k] = __fdividef(o[k], 1.0f + __expf(-o[k]));
-            }
-        }
-        uint32_t h0, l0, h1, l1;
-        split2(o[0], o[1], h0, l0); split2(o[2], o[3], h1, l1);
-        reinterpret_cast<uint2 *>(hi)[e] = make_uint2(h0, h1);
-        reinterpret_cast<uint2 *>(lo)[e] = make_uint2(l0, l1);
-    }
-}
-
 }  // namespace
 
 // CTAs per image of gn_apply_split_kernel: each thread should own ~4 8-channel groups (one unrolled iteration) and the
@@ -673,33 +566,5 @@ extern "C" int sgam_stem_conv_in(const float *x, const uint8_t *mask, const floa
     const size_t smem = (size_t)(BH + 2) * (BW + 2) * sizeof(float4);
     SGAM_PDL_LAUNCH(SGAM_PDL_MISC, stem_conv_in_kernel, dim3(tiles, B), 128, smem, (cudaStream_t)stream, x, mask, w1, b1, w3, b3, y, gn_partial, H, W,
                     BW, BH, tiles_x, tiles);
-    return SGAM_OK;
-}
-
-// Finish of a deferred split-K convolution (sgam_conv2d_tc with defer_reduce): y = sum of the ksplit partials (+ bias)
-// (+ residual), and in the same launch the consumer's operand: mode 2 = GroupNorm(32, C, eps 1e-6) (+ swish) -> split bf16,
-// mode 1 = plain split bf16, mode 0 = y only.  ws [ksplit][B*HW*C]; C in {128, 256, 512, 1024}.
-extern "C" int sgam_splitk_finish(const float *ws, int ksplit, const float *bias, const float *residual, float *y, const float *gamma,
-                                  const float *beta, void *hi, void *lo, int B, long long HW, int C, int mode, int swish, void *stream) {
-    SGAM_REQUIRE(ws && y && ksplit >= 1 && B > 0 && HW > 0, "splitk_finish: bad arguments");
-    SGAM_REQUIRE(C == 128 || C == 256 || C == 512 || C == 1024, "splitk_finish: C=%d must be 128, 256, 512 or 1024", C);
-    SGAM_REQUIRE(mode == 0 || (hi && lo), "splitk_finish: modes 1 / 2 write the split planes");
-    SGAM_REQUIRE(mode != 2 || (gamma && beta), "splitk_finish: mode 2 needs gamma / beta");
-    static bool configured = false;
-    if (!configured) {
-        SGAM_CUDA_OK(cudaFuncSetAttribute(splitk_finish_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        configured = true;
-    }
-    int CL = 16;                                              // CTAs per image: the largest power of two <= 16 that divides HW
-    while (CL > 1 && (HW % CL != 0)) CL >>= 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(B * CL)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    ++g_sgam_launches;
-    SGAM_CUDA_OK(cudaLaunchKernelEx(&cfg, splitk_finish_kernel, ws, (long long)B * HW * C, ksplit, bias, residual, y, gamma, beta,
-                                    (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, mode, swish));
     return SGAM_OK;
 }

@@ -354,10 +354,6 @@ def split_bf16(x, upsample=0):
     """fp32 NHWC [B,H,W,C] -> (hi, lo) bf16 [B,H<<up,W<<up,C] with x = hi + lo (+ fused nearest x2 up-sampling)."""
     lib = _lib.load()
     _chk(x, name="x")
-    if getattr(x, "pending", None) is not None:
-        if not upsample:
-            return _finish(x, 1)                    # split-K reduction + split in one launch
-        materialize(x)
     B, H, W, C = x.shape
     hi, lo = _bf16_pair((B, H << upsample, W << upsample, C), x.device)
     _lib.check(lib.sgam_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, H, W, C, int(upsample), _stream()),
@@ -380,8 +376,6 @@ def groupnorm_split(x, gamma, beta, swish, workspace=None):
     """GroupNorm(32, C, eps=1e-6) (+ swish) -> (hi, lo) bf16 NHWC."""
     lib = _lib.load()
     _chk(x, name="x"), _chk(gamma, name="gamma"), _chk(beta, name="beta")
-    if getattr(x, "pending", None) is not None:
-        return _finish(x, 2, gamma, beta, swish)    # split-K reduction + GroupNorm statistics + apply in one launch
     B, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * C)
     hi, lo = _bf16_pair(tuple(x.shape), x.device)
@@ -419,12 +413,10 @@ def tc_supported_conv(H, W, Cin, Cout, ksize, stride):
 
 
 def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=False, out_f32=True, out_split=False, nsplit=3,
-              gn_stats=False, defer=False):
+              gn_stats=False):
     """Conv on tcgen05 (stride 1 symmetric pad, or stride 2 = Downsample).  x = (hi, lo) bf16 [B,H,W,Cin];
     w = (hi, lo) bf16 [ceil32(Cout), k*k*Cin]; bias fp32 [Cout].  Returns fp32 y [B,Ho,Wo,Cout] (or [B,Cout,Ho,Wo] with
-    out_nchw) and/or the (hi, lo) pair, as requested.  defer=True: when the library splits the K loop, y comes back
-    PENDING (`y.pending`: the partial tensors, bias and residual) and is finished by its first consumer --
-    groupnorm_split / split_bf16 fuse the reduction with their own pass, `materialize` just reduces."""
+    out_nchw) and/or the (hi, lo) pair, as requested."""
     lib = _lib.load()
     x_hi, x_lo = x
     w_hi, w_lo = w
@@ -438,14 +430,13 @@ def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=
     y = torch.empty((B, Cout, Ho, Wo) if out_nchw else (B, Ho, Wo, Cout), device=x_hi.device) if out_f32 else None
     pair = _bf16_pair((B, Ho, Wo, Cout), x_hi.device) if out_split else (None, None)
     if residual is not None:
-        _chk(materialize(residual), name="residual")
+        _chk(residual, name="residual")
     partial = splitk = partial64 = None
-    defer = bool(defer) and Cout in (128, 256, 512, 1024)
     if out_f32 and not out_split and not out_nchw and Cout % 32 == 0:
         n_ws = lib.sgam_conv2d_tc_splitk_floats(B, H, W, Cin, Cout, ksize, stride)
         if n_ws > 0:                    # under-filled grid: split the K loop; the reduce kernel also takes the statistics
             splitk = torch.empty(n_ws, device=x_hi.device)
-            if gn_stats and Cout % 128 == 0 and Cout <= 1024 and not defer:
+            if gn_stats and Cout % 128 == 0 and Cout <= 1024:
                 partial64 = torch.empty(B * lib.sgam_gn_splits(Ho * Wo) * 64, dtype=torch.float64, device=x_hi.device)
     if splitk is None and gn_stats and out_f32 and not out_nchw and Cout % 128 == 0 and Cout <= 512:
         partial = torch.empty(lib.sgam_tc_gn_partial_floats(B, Ho, Wo), device=x_hi.device)
@@ -453,39 +444,15 @@ def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=
     _lib.check(lib.sgam_conv2d_tc(x_hi.data_ptr(), x_lo.data_ptr(), w_hi.data_ptr(), w_lo.data_ptr(), _ptr(bias),
                                   _ptr(residual), _ptr(y), _ptr(pair[0]), _ptr(pair[1]), B, H, W, Cin, Cout, ksize,
                                   stride, int(out_nchw), nsplit, _ptr(partial), _ptr(splitk), _ptr(partial64),
-                                  ctypes.byref(written), int(defer and splitk is not None), _stream()), "sgam_conv2d_tc")
+                                  ctypes.byref(written), _stream()), "sgam_conv2d_tc")
     # the library reports which statistics buffer it filled; attach exactly that one (never a guess)
-    if (written.value & 0xff) == 3:     # split-K GEMM only: y is finished by its first consumer (sgam_splitk_finish)
-        y.pending = dict(ws=splitk, ksplit=written.value >> 8, bias=bias, residual=residual)
-    elif written.value == 1:
+    if written.value == 1:
         y.gn_partial = partial          # GroupNorm statistics of y, fused into the epilogue (consumed by groupnorm_split)
     elif written.value == 2:
         y.gn_partial64 = partial64      # ... or into the split-K reduction
     if out_f32 and out_split:
         return y, pair
     return y if out_f32 else pair
-
-
-def _finish(y, mode, gamma=None, beta=None, swish=False):
-    """sgam_splitk_finish on a pending conv output: y = sum of the split-K partials (+ bias, + residual) and, in the same launch,
-    the consumer's operand (mode 2: GroupNorm (+ swish) -> split bf16; mode 1: plain split; mode 0: y only)."""
-    lib = _lib.load()
-    pend = y.pending
-    B, C = y.shape[0], y.shape[-1]
-    HW = y.numel() // (B * C)
-    pair = _bf16_pair(tuple(y.shape), y.device) if mode else (None, None)
-    _lib.check(lib.sgam_splitk_finish(pend["ws"].data_ptr(), pend["ksplit"], _ptr(pend["bias"]), _ptr(pend["residual"]), y.data_ptr(),
-                                      _ptr(gamma), _ptr(beta), _ptr(pair[0]), _ptr(pair[1]), B, HW, C, mode, int(swish), _stream()),
-               "sgam_splitk_finish")
-    del y.pending
-    return pair
-
-
-def materialize(y):
-    """Make sure a conv output holds its values (finish a deferred split-K reduction); returns y."""
-    if y is not None and getattr(y, "pending", None) is not None:
-        _finish(y, 0)
-    return y
 
 
 def gemm_nt_tc(a, b, bias_m=None, alpha=1.0, out_f32=True, out_split=False, nsplit=3):

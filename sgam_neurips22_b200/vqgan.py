@@ -36,7 +36,6 @@ class VQGANEngine:
         self.fused_head = os.environ.get("SGAM_FUSED_HEAD", "1") != "0"
         self.subpixel = os.environ.get("SGAM_SUBPIXEL", "1") != "0"
         self.fused_stem = os.environ.get("SGAM_FUSED_STEM", "1") != "0"
-        self.defer_splitk = os.environ.get("SGAM_DEFER_SPLITK", "1") != "0"
         self.p = {}
         self.wsplit = {}
         self.load_state_dict(state_dict)
@@ -85,12 +84,10 @@ class VQGANEngine:
     # ------------------------------------------------------------------ blocks (NHWC)
     def conv(self, name, x, **kw):
         """fp32 CUDA-core conv (sgam_conv2d)."""
-        if kw.get("residual") is not None:
-            ops.materialize(kw["residual"])
-        return ops.conv2d(ops.materialize(x), self.p[f"{name}.weight"], self.p[f"{name}.bias"], **kw)
+        return ops.conv2d(x, self.p[f"{name}.weight"], self.p[f"{name}.bias"], **kw)
 
     def norm(self, name, x, swish):
-        return ops.groupnorm(ops.materialize(x), self.p[f"{name}.weight"], self.p[f"{name}.bias"], swish)
+        return ops.groupnorm(x, self.p[f"{name}.weight"], self.p[f"{name}.bias"], swish)
 
     def norm_split(self, name, x, swish):
         return ops.groupnorm_split(x, self.p[f"{name}.weight"], self.p[f"{name}.bias"], swish)
@@ -106,7 +103,6 @@ class VQGANEngine:
     def conv_tc(self, name, xs, ksize, **kw):
         """tcgen05 conv on a split-bf16 activation pair."""
         kw.setdefault("gn_stats", True)       # nearly every fp32 conv output feeds a GroupNorm: fuse its statistics
-        kw.setdefault("defer", self.defer_splitk)   # split-K layers: the first consumer finishes the reduction in its own launch
         return ops.conv2d_tc(xs, self.wsplit[name], self.p[f"{name}.bias"], ksize=ksize, nsplit=self.nsplit,
                              cout=self.p[f"{name}.weight"].shape[0], **kw)
 
@@ -239,7 +235,7 @@ class VQGANEngine:
         else:
             h = self.conv("encoder.conv_in", ops.stem_conv(x, mask, self.p["conv_in.weight"], self.p["conv_in.bias"]), ksize=3)
         h = self.encoder(h)
-        return ops.materialize(self.conv_from_f32("quant_conv", h, 1))
+        return self.conv_from_f32("quant_conv", h, 1)
 
     def quantize(self, pre_quant):
         """quantize.py:275-319 / :344-381 (topk=1): NHWC latent -> idx [B,h,w] int64, z_q NHWC."""
@@ -252,7 +248,7 @@ class VQGANEngine:
 
     def decode(self, z_q):
         """model.py:131-134: NHWC quantised latent -> dec [B,4,H,W] NCHW."""
-        return ops.materialize(self.decoder(self.conv_from_f32("post_quant_conv", z_q, 1)))
+        return self.decoder(self.conv_from_f32("post_quant_conv", z_q, 1))
 
     def embed_code(self, idx):
         """Codebook gather for decode_code (model.py:136-139): idx [B,h,w] -> NHWC latent."""
