@@ -251,6 +251,51 @@ class StepHarness:
         self.pin_depth.copy_(depth, non_blocking=True)
         torch.cuda.current_stream().synchronize()                      # the caller reads the frame before the next step
 
+    # -- the same end-to-end step with the NEXT step's source frames uploaded on a copy stream while this step computes -------
+    def e2e_prefetch_init(self):
+        keys = ("src_imgs", "src_depths")
+        self.copy_stream = torch.cuda.Stream()
+        self.stage = [{k: torch.empty(self.host[k].shape, dtype=self.host[k].dtype, device=self.dev) for k in keys} for _ in range(2)]
+        self.stage_ready = [torch.cuda.Event() for _ in range(2)]
+        self.stage_free = [torch.cuda.Event() for _ in range(2)]
+        self.pin_out = [(self.pin_rgb, self.pin_depth), (torch.empty_like(self.pin_rgb).pin_memory(), torch.empty_like(self.pin_depth).pin_memory())]
+        self.out_done = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+        torch.cuda.synchronize()
+        self._prefetch(0)
+
+    def _prefetch(self, i):
+        j = i % 2
+        with torch.cuda.stream(self.copy_stream):
+            if i >= 2:
+                self.copy_stream.wait_event(self.stage_free[j])        # step i-2's splat has consumed this buffer
+            for k, d in self.stage[j].items():
+                d.copy_(self.host[k], non_blocking=True)
+            self.stage_ready[j].record(self.copy_stream)
+
+    def e2e_prefetch(self):
+        """Step i: upload step i+1's source frames (copy stream), run step i through the public API on the frames uploaded
+        one step earlier, copy its frame to pinned host memory, then wait for frame i-1 (the host reads every frame, one
+        step behind the device).  Copies per step are those of `e2e`."""
+        i = self.k
+        j = i % 2
+        self.k += 1
+        self._prefetch(i + 1)
+        main = torch.cuda.current_stream()
+        main.wait_event(self.stage_ready[j])
+        b = dict(self.api_batch)
+        b.update(self.stage[j])
+        x, _, mask, _ = self.model.get_x(b, self.ds, return_extrapolation_mask=True, no_depth_range=True, parallel=True)
+        self.stage_free[j].record(main)
+        decs, _, pre, quants = self.model(x, topk=1, extrapolation_mask=mask, get_pre_quantized_feature=True,
+                                          get_quantized_feature=True, sample_number=1)
+        rgb, depth = self.ops.frame_outputs(decs[0][0], self.ds, rgb_u8=self.out_rgb, depth=self.out_depth)
+        self.pin_out[j][0].copy_(rgb, non_blocking=True)
+        self.pin_out[j][1].copy_(depth, non_blocking=True)
+        self.out_done[j].record(main)
+        if i > 0:
+            self.out_done[1 - j].synchronize()
+
     def digest(self):
         """SHA-256 of the step's outputs (uint8 RGB + fp32 depth bytes) after one resident run."""
         self.run()
@@ -365,8 +410,21 @@ class StepHarness:
                         "decoder head runs on the FP32 pipes (gn_head_conv) and is not part of this figure"}
 
 
-def measure(h, steps, warmup, world):
-    """-> (value leg ms, e2e leg ms, e2e steps)."""
+def e2e_record(serial_value, serial_ms, pf_value, pf_ms, h):
+    """The end-to-end record: the better of the two legs is the value, both are reported.  Same copies per step in both."""
+    api = "VQModel.get_x + VQModel.forward(topk=1) + frame_outputs, pinned host buffers"
+    serial = {"value": serial_value, "ms_per_step": serial_ms,
+              "mode": "upload, compute, read back and host wait, one step at a time"}
+    prefetch = {"value": pf_value, "ms_per_step": pf_ms,
+                "mode": "step i+1's source frames are uploaded on a copy stream while step i computes; the host reads every "
+                        "frame one step behind the device (double-buffered pinned output)"}
+    best = prefetch if pf_value > serial_value else serial
+    return {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": int(h.h2d), "d2h_bytes_per_step": int(h.d2h),
+            "ms_per_step": best["ms_per_step"], "api": api, "mode": best["mode"], "serial": serial, "prefetch": prefetch}
+
+
+def measure(h, steps, warmup, world, prefetch=False):
+    """-> (value leg ms, e2e leg ms, e2e steps); prefetch=True adds the copy-stream variant: (.., prefetch leg ms)."""
     for _ in range(warmup):
         h.run()
     ms = time_steps(h.run, steps, world)
@@ -374,7 +432,13 @@ def measure(h, steps, warmup, world):
         h.e2e()
     e2e_steps = max(3, min(steps, 20))
     ms_e2e = time_steps(h.e2e, e2e_steps, world)
-    return ms, ms_e2e, e2e_steps
+    if not prefetch:
+        return ms, ms_e2e, e2e_steps
+    h.e2e_prefetch_init()
+    for _ in range(warmup):
+        h.e2e_prefetch()
+    ms_pf = time_steps(h.e2e_prefetch, e2e_steps, world)
+    return ms, ms_e2e, e2e_steps, ms_pf
 
 
 def latest_traffic():
@@ -540,6 +604,11 @@ def main():
     e2e_steps = max(3, min(args.steps, 20))
     ms_e2e = time_steps(h.e2e, e2e_steps, world)
     e2e_value = B * world * e2e_steps / (ms_e2e / 1000.0)
+    h.e2e_prefetch_init()
+    for _ in range(args.warmup):
+        h.e2e_prefetch()
+    ms_pf = time_steps(h.e2e_prefetch, e2e_steps, world)
+    pf_value = B * world * e2e_steps / (ms_pf / 1000.0)
     roof = h.roofline(peaks, ms / args.steps, dump=args.dump_gemm if rank == 0 else None)
     traffic, traffic_src = latest_traffic() if (ds == "clevr-infinite" and B == 8 and res == 256) else (None, None)
     roof["traffic"], roof["traffic_source"] = traffic, traffic_src
@@ -737,8 +806,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (tensor-core products as 3-term split bf16, fp32 accumulate)", "data": "synthetic", "config": cfg,
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h.h2d), "d2h_bytes_per_step": int(h.d2h),
-                    "ms_per_step": ms_e2e / e2e_steps, "api": "VQModel.get_x + VQModel.forward(topk=1) + frame_outputs, pinned host buffers"},
+            "e2e": e2e_record(e2e_value, ms_e2e / e2e_steps, pf_value, ms_pf / e2e_steps, h),
             "gpu_launches": h.launches_per_step * args.steps, "gpu_launches_per_step": h.launches_per_step,
             "roofline": roof,
             "kernels": {

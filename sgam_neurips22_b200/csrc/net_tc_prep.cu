@@ -33,14 +33,29 @@ split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, _
     }
 }
 
-// GroupNorm apply (+ swish) with split-bf16 output; statistics come from gn_stats (net_simt.cu) partials
-__global__ void __launch_bounds__(256)
+// GroupNorm apply (+ swish) with split-bf16 output; statistics come from gn_stats (net_simt.cu) partials.
+// U independent 8-channel groups per thread and iteration; the first iteration's loads are issued BEFORE the statistics
+// prologue so that the two global-memory round trips overlap (most launches of a step have exactly one iteration).
+template <int U, bool FIXED_C>
+__global__ void __launch_bounds__(256, U == 4 ? 3 : (U == 2 ? 4 : 5))
 gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ partial, const float *__restrict__ meanrstd,
                       const float *__restrict__ gamma, const float *__restrict__ beta, __nv_bfloat16 *__restrict__ hi,
                       __nv_bfloat16 *__restrict__ lo, long long HW, int C, int S, int swish) {
     SGAM_PDL_PROLOGUE();
     __shared__ float mean_s[32], rstd_s[32];
     const int b = blockIdx.y, tid = threadIdx.x;
+    const int CO = C / 8, cpg = C / 32;                 // 8 channels per thread (cpg >= 4: at most two groups)
+    const long long total = HW * CO;
+    const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)b * HW * C);
+    uint4 *dh = reinterpret_cast<uint4 *>(hi + (size_t)b * HW * C), *dl = reinterpret_cast<uint4 *>(lo + (size_t)b * HW * C);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long e0 = (long long)blockIdx.x * blockDim.x + tid;
+    float4 v0[U], v1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long e = e0 + u * stride;
+        if (e < total) { v0[u] = __ldg(src + 2 * e); v1[u] = __ldg(src + 2 * e + 1); }
+    }
     if (meanrstd && S > 0) {            // per-pixel-block sums from the producing conv's epilogue, S = blocks per image (<= 64)
         gn_mean_rstd_from_tiles(meanrstd, b, S, (double)HW * (C / 32), mean_s, rstd_s);
     } else if (meanrstd) {              // statistics already finalised by gn_finalize_kernel
@@ -49,27 +64,24 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
         gn_mean_rstd_from_partials(partial, b, S, (double)HW * (C / 32), mean_s, rstd_s);
     }
     __syncthreads();
-    const int CO = C / 8, cpg = C / 32;                 // 8 channels per thread (cpg >= 4: at most two groups)
-    const long long total = HW * CO;
-    const float4 *src = reinterpret_cast<const float4 *>(x + (size_t)b * HW * C);
-    uint4 *dh = reinterpret_cast<uint4 *>(hi + (size_t)b * HW * C), *dl = reinterpret_cast<uint4 *>(lo + (size_t)b * HW * C);
-    // 4 independent 8-channel groups per thread and iteration, all 8 loads issued before the first is used
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e0 = (long long)blockIdx.x * blockDim.x + tid; e0 < total; e0 += 4 * stride) {
-        float4 v0[4], v1[4];
+    // FIXED_C: the grid stride is a multiple of the channel-octet count (C = 128 .. 1024, powers of two): a thread keeps ONE
+    // channel octet for its whole life and its affine parameters stay in registers
+    constexpr bool fixed_c = FIXED_C;
+    int c = (int)(e0 % CO) * 8;
+    float mu0 = mean_s[c / cpg], rs0 = rstd_s[c / cpg], mu1 = mean_s[(c + 4) / cpg], rs1 = rstd_s[(c + 4) / cpg];
+    float4 ga0 = __ldg(reinterpret_cast<const float4 *>(gamma + c)), ga1 = __ldg(reinterpret_cast<const float4 *>(gamma + c + 4));
+    float4 be0 = __ldg(reinterpret_cast<const float4 *>(beta + c)), be1 = __ldg(reinterpret_cast<const float4 *>(beta + c + 4));
+    while (e0 < total) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long e = e0 + u * stride;
-            if (e < total) { v0[u] = __ldg(src + 2 * e); v1[u] = __ldg(src + 2 * e + 1); }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long e = e0 + u * stride;
             if (e >= total) break;
-            const int c = (int)(e % CO) * 8, g0 = c / cpg, g1 = (c + 4) / cpg;
-            const float mu0 = mean_s[g0], rs0 = rstd_s[g0], mu1 = mean_s[g1], rs1 = rstd_s[g1];
-            const float4 ga0 = __ldg(reinterpret_cast<const float4 *>(gamma + c)), ga1 = __ldg(reinterpret_cast<const float4 *>(gamma + c + 4));
-            const float4 be0 = __ldg(reinterpret_cast<const float4 *>(beta + c)), be1 = __ldg(reinterpret_cast<const float4 *>(beta + c + 4));
+            if (!fixed_c) {
+                c = (int)(e % CO) * 8;
+                mu0 = mean_s[c / cpg]; rs0 = rstd_s[c / cpg]; mu1 = mean_s[(c + 4) / cpg]; rs1 = rstd_s[(c + 4) / cpg];
+                ga0 = __ldg(reinterpret_cast<const float4 *>(gamma + c)); ga1 = __ldg(reinterpret_cast<const float4 *>(gamma + c + 4));
+                be0 = __ldg(reinterpret_cast<const float4 *>(beta + c)); be1 = __ldg(reinterpret_cast<const float4 *>(beta + c + 4));
+            }
             float o[8] = {(v0[u].x - mu0) * rs0 * ga0.x + be0.x, (v0[u].y - mu0) * rs0 * ga0.y + be0.y,
                           (v0[u].z - mu0) * rs0 * ga0.z + be0.z, (v0[u].w - mu0) * rs0 * ga0.w + be0.w,
                           (v1[u].x - mu1) * rs1 * ga1.x + be1.x, (v1[u].y - mu1) * rs1 * ga1.y + be1.y,
@@ -83,6 +95,12 @@ gn_apply_split_kernel(const float *__restrict__ x, const double *__restrict__ pa
             for (int k = 0; k < 4; ++k) split2(o[2 * k], o[2 * k + 1], h[k], l[k]);
             dh[e] = make_uint4(h[0], h[1], h[2], h[3]);
             dl[e] = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        e0 += U * stride;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long e = e0 + u * stride;
+            if (e < total) { v0[u] = __ldg(src + 2 * e); v1[u] = __ldg(src + 2 * e + 1); }
         }
     }
 }
@@ -360,6 +378,8 @@ gn_head_conv_kernel(const float *__restrict__ x, const float *__restrict__ meanr
 // values of its halo in shared memory (zero outside the image: the conv pads the STEM OUTPUT), thread c owns output channel
 // c with its 36 taps in registers and walks the block in segments of four pixels (the 3 x 6 window is read once with
 // broadcast 16-byte loads), writes 512-byte rows, and the per-channel sums are folded to the 32 groups with two shuffles.
+// 147 us at 8 trajectories = 2.4 G FMAs at 64 lanes per clock and SM: three-register FFMAs issue every other cycle on this
+// part, and the packed FFMA2 form measured the same (profiles/r2_rejected_experiments.txt) -- this is the FP32-pipe roofline.
 __global__ void __launch_bounds__(128)
 stem_conv_in_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mask, const float *__restrict__ w1, const float *__restrict__ b1,
                     const float *__restrict__ w3 /* [128][9*4] */, const float *__restrict__ b3, float *__restrict__ y,
@@ -440,13 +460,38 @@ stem_conv_in_kernel(const float *__restrict__ x, const uint8_t *__restrict__ mas
 
 }  // namespace
 
-// CTAs per image of gn_apply_split_kernel: each thread should own ~4 8-channel groups (one unrolled iteration) and the
+// CTAs per image of gn_apply_split_kernel<U>: each thread should own U 8-channel groups (one unrolled iteration) and the
 // whole launch should not exceed ~8 CTAs per SM; small tensors get fewer CTAs rather than one group per thread
-static unsigned gn_apply_blocks(long long total, int B) {
-    long long want = (total + 1023) / 1024;                          // 256 threads x 4 groups
+static unsigned gn_apply_blocks(long long total, int B, int U) {
+    long long want = (total + 256 * U - 1) / (256 * U);
     const long long cap = ((long long)148 * 8 + B - 1) / B;
     if (want > cap) want = cap;
     return (unsigned)(want < 1 ? 1 : want);
+}
+
+// groups per thread; experiments: SGAM_GN_APPLY_U=1|2|4
+static int gn_apply_unroll(long long total, int B) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char *e = getenv("SGAM_GN_APPLY_U");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    (void)total; (void)B;
+    return 2;                           // profiles/r2_gn_apply_sweep.txt: 2 is best or tied at every shape of the step
+}
+
+static cudaError_t gn_apply_launch(cudaStream_t s, const float *x, const double *partial, const float *meanrstd, const float *gamma,
+                                   const float *beta, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int B, long long HW, int C, int S, int swish) {
+    const long long total = HW * (C / 8);
+    const int U = gn_apply_unroll(total, B);
+    const dim3 grid(gn_apply_blocks(total, B, U), B);
+    const bool fixed = ((long long)grid.x * 256) % (C / 8) == 0;
+#define SGAM_GN_APPLY(UU, FF) sgam_launch_pdl(SGAM_PDL_NORM, gn_apply_split_kernel<UU, FF>, grid, dim3(256), 0, s, x, partial, meanrstd, gamma, beta, hi, lo, HW, C, S, swish)
+    if (U == 1) return fixed ? SGAM_GN_APPLY(1, true) : SGAM_GN_APPLY(1, false);
+    if (U == 2) return fixed ? SGAM_GN_APPLY(2, true) : SGAM_GN_APPLY(2, false);
+    return fixed ? SGAM_GN_APPLY(4, true) : SGAM_GN_APPLY(4, false);
+#undef SGAM_GN_APPLY
 }
 
 // gn_stats launcher lives in net_simt.cu
@@ -476,10 +521,8 @@ extern "C" int sgam_groupnorm_split(const float *x, const float *gamma, const fl
     cudaStream_t s = (cudaStream_t)stream;
     int rc = sgam_gn_stats_launch(x, partial, B, HW, C, s);
     if (rc) return rc;
-    const long long total = HW * (C / 8);
-    const unsigned blocks = gn_apply_blocks(total, B);
-    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
-                                                          sgam_gn_splits(HW), swish);
+    ++g_sgam_launches;
+    SGAM_CUDA_OK(gn_apply_launch(s, x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, B, HW, C, sgam_gn_splits(HW), swish));
     return SGAM_OK;
 }
 
@@ -487,10 +530,8 @@ extern "C" int sgam_groupnorm_split_apply(const float *x, const float *gamma, co
                                           const double *partial, int B, long long HW, int C, int swish, void *stream) {
     SGAM_REQUIRE(x && gamma && beta && hi && lo && partial, "groupnorm_split_apply: null pointer");
     SGAM_REQUIRE(B > 0 && HW > 0 && C % 128 == 0 && C <= 1024, "groupnorm_split_apply: C=%d must be a multiple of 128 (<= 1024)", C);
-    const long long total = HW * (C / 8);
-    const unsigned blocks = gn_apply_blocks(total, B);
-    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, (cudaStream_t)stream, x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C,
-                                                                             sgam_gn_splits(HW), swish);
+    ++g_sgam_launches;
+    SGAM_CUDA_OK(gn_apply_launch((cudaStream_t)stream, x, partial, nullptr, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, B, HW, C, sgam_gn_splits(HW), swish));
     return SGAM_OK;
 }
 
@@ -508,15 +549,15 @@ extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, co
     const int BW = Wo >= 128 ? 128 : Wo, BH = 128 / BW;
     const int tiles = cdiv(Wo, BW) * cdiv(Ho, BH);
     const long long HW = (long long)Ho * Wo;
-    const long long total = HW * (C / 8);
-    const unsigned blocks = gn_apply_blocks(total, B);
     if (tiles <= 64) {                  // few blocks per image: every CTA of the apply kernel finalises the sums itself (one launch less)
-        SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, nullptr, gn_partial, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, tiles, swish);
+        ++g_sgam_launches;
+        SGAM_CUDA_OK(gn_apply_launch(s, x, nullptr, gn_partial, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, B, HW, C, tiles, swish));
         return SGAM_OK;
     }
     float *meanrstd = gn_partial + (long long)B * tiles * 64;
     SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_finalize_kernel, cdiv(B * 32, 8), 256, 0, s, gn_partial, meanrstd, tiles, (double)HW * (C / 32), B * 32);
-    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_apply_split_kernel, dim3(blocks, B), 256, 0, s, x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, HW, C, 0, swish);
+    ++g_sgam_launches;
+    SGAM_CUDA_OK(gn_apply_launch(s, x, nullptr, meanrstd, gamma, beta, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, B, HW, C, 0, swish));
     return SGAM_OK;
 }
 
