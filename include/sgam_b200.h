@@ -254,9 +254,20 @@ int sgam_attention_tc_supported(int B, int T, int C);
  * (1 = no split, no workspace); the workspace holds sgam_attention_tc_workspace_bytes(B, T, kv_splits) bytes. */
 int sgam_attention_tc_splits(int B, int T);
 size_t sgam_attention_tc_workspace_bytes(int B, int T, int kv_splits);
+/* ld_qk: elements between consecutive token rows of q and of k (0 = C, dense); 2C when q and k are the two column halves of
+ * sgam_qkv_tc's [B,T,2C] output. */
 int sgam_attention_tc(const void *q_hi, const void *q_lo, const void *k_hi, const void *k_lo, const void *vt_hi,
                       const void *vt_lo, void *o_hi, void *o_lo, int B, int T, int C, float scale, int kv_splits,
-                      void *workspace, void *stream);
+                      void *workspace, int ld_qk, void *stream);
+
+/* The q, k and v projections of an AttnBlock (three 1x1 convs of the same GroupNorm output, diffusionmodules/model.py:
+ * 158-175) as ONE tcgen05 implicit GEMM with 3C output columns.  x [B,H,W,C] split bf16; w [3C, C] split bf16 = the rows of
+ * q.weight, k.weight, v.weight; bias [3C] fp32.  qk [B, H*W, 2C] split bf16 (q = columns [0,C), k = [C,2C)); vt [B, C, H*W]
+ * split bf16 = V^T, stored transposed by the epilogue (the K-major operand sgam_attention_tc / sgam_gemm_nt_tc expect).
+ * Needs C % 128 == 0, W % 32 == 0, H*W % 128 == 0 and a shape sgam_tc_supported_conv accepts. */
+int sgam_qkv_tc_supported(int B, int H, int W, int C);
+int sgam_qkv_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias, void *qk_hi,
+                void *qk_lo, void *vt_hi, void *vt_lo, int B, int H, int W, int C, int nsplit, void *stream);
 
 /* Batched C = alpha * A . B^T (+ bias_m[row]) on tensor cores.  A [batch|1, M, K], B [batch|1, N, K] split-bf16
  * (a_batched / b_batched say whether the operand has the batch dimension); output fp32 C and/or split-bf16. */

@@ -62,7 +62,9 @@ SIGNATURES = {
     "sgam_attention_tc_supported": (c_i, [c_i, c_i, c_i]),
     "sgam_attention_tc_splits": (c_i, [c_i, c_i]),
     "sgam_attention_tc_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
-    "sgam_attention_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_p]),
+    "sgam_attention_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_i, c_p]),
+    "sgam_qkv_tc_supported": (c_i, [c_i, c_i, c_i, c_i]),
+    "sgam_qkv_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sgam_unproject_points": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     "sgam_tsdf_volume_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
     "sgam_tsdf_block_bytes": (c_sz, [c_i]),

@@ -438,17 +438,18 @@ extern "C" size_t sgam_attention_tc_workspace_bytes(int B, int T, int kv_splits)
 
 extern "C" int sgam_attention_tc(const void *q_hi, const void *q_lo, const void *k_hi, const void *k_lo, const void *vt_hi,
                                  const void *vt_lo, void *o_hi, void *o_lo, int B, int T, int C, float scale, int kv_splits,
-                                 void *workspace, void *stream) {
+                                 void *workspace, int ld_qk, void *stream) {
     SGAM_REQUIRE(q_hi && q_lo && k_hi && k_lo && vt_hi && vt_lo && o_hi && o_lo, "attention_tc: null pointer");
     SGAM_REQUIRE(sgam_attention_tc_supported(B, T, C), "attention_tc: needs C == 256 and T %% 256 == 0 (B=%d T=%d C=%d)", B, T, C);
     SGAM_REQUIRE(scale > 0.0f, "attention_tc: scale must be positive");
     SGAM_REQUIRE(kv_splits >= 1 && (T / AT_BN) % kv_splits == 0 && (kv_splits == 1 || workspace), "attention_tc: kv_splits %d must divide the %d key tiles (and needs a workspace)", kv_splits, T / AT_BN);
+    SGAM_REQUIRE(ld_qk == 0 || (ld_qk >= C && ld_qk % 8 == 0), "attention_tc: ld_qk %d must be 0 (dense) or a multiple of 8 >= C", ld_qk);
     CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo, mv_hi, mv_lo;
     const long long qk_dims[3] = {C, T, B}, v_dims[3] = {T, C, B};
     const int q_box[3] = {64, 128, 1}, k_box[3] = {64, 64, 1}, v_box[3] = {64, 128, 1};
     int rc;
-    if ((rc = make_map(&mq_hi, q_hi, 3, qk_dims, q_box)) || (rc = make_map(&mq_lo, q_lo, 3, qk_dims, q_box)) ||
-        (rc = make_map(&mk_hi, k_hi, 3, qk_dims, k_box)) || (rc = make_map(&mk_lo, k_lo, 3, qk_dims, k_box)) ||
+    if ((rc = make_map(&mq_hi, q_hi, 3, qk_dims, q_box, nullptr, ld_qk)) || (rc = make_map(&mq_lo, q_lo, 3, qk_dims, q_box, nullptr, ld_qk)) ||
+        (rc = make_map(&mk_hi, k_hi, 3, qk_dims, k_box, nullptr, ld_qk)) || (rc = make_map(&mk_lo, k_lo, 3, qk_dims, k_box, nullptr, ld_qk)) ||
         (rc = make_map(&mv_hi, vt_hi, 3, v_dims, v_box)) || (rc = make_map(&mv_lo, vt_lo, 3, v_dims, v_box)))
         return rc;
     AttnParams p;

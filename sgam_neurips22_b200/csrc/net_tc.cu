@@ -451,6 +451,49 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
     return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, (cudaStream_t)stream);
 }
 
+// ---- AttnBlock q / k / v projections (three 1x1 convs of the same normalised tensor, diffusionmodules/model.py:158-175) as
+// ONE implicit GEMM with N = 3C: the operand is read once and one launch replaces three.  w [3C, C] = rows of q.weight, k.weight,
+// v.weight; bias [3C].  qk [B, H*W, 2C] split bf16 (q = columns [0, C), k = [C, 2C): the attention kernel reads both with a
+// row pitch of 2C); vt [B, C, H*W] split bf16 = V^T, written transposed by the epilogue (tc_common.cuh).
+extern "C" int sgam_qkv_tc_supported(int B, int H, int W, int C) {
+    return B > 0 && H > 0 && W > 0 && C % 128 == 0 && W % 32 == 0 && ((long long)H * W) % 128 == 0 &&
+           sgam_tc_supported_conv(H, W, C, 3 * C, 1, 1);
+}
+
+extern "C" int sgam_qkv_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias, void *qk_hi,
+                           void *qk_lo, void *vt_hi, void *vt_lo, int B, int H, int W, int C, int nsplit, void *stream) {
+    SGAM_REQUIRE(x_hi && x_lo && w_hi && w_lo && bias && qk_hi && qk_lo && vt_hi && vt_lo, "qkv_tc: null pointer");
+    SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "qkv_tc: nsplit must be 1 or 3");
+    SGAM_REQUIRE(sgam_qkv_tc_supported(B, H, W, C), "qkv_tc: unsupported shape B=%d H=%d W=%d C=%d", B, H, W, C);
+    const int N = 3 * C;
+    TcParams p{};
+    p.Ho = H; p.Wo = W; p.taps = 1; p.ks = 1; p.pad = 0; p.stride = 1; p.kblocks_per_tap = C / 64;
+    p.N = N; p.n_valid = N; p.nsplit = nsplit; p.a_batched = 1; p.b_batched = 0; p.alpha = 1.0f; p.bias_n = bias;
+    p.D_hi = (__nv_bfloat16 *)qk_hi; p.D_lo = (__nv_bfloat16 *)qk_lo; p.ldd = 2 * C; p.d_batch_stride = (long long)H * W * 2 * C;
+    p.vt_col0 = 2 * C; p.vt_T = (long long)H * W; p.vt_hi = (__nv_bfloat16 *)vt_hi; p.vt_lo = (__nv_bfloat16 *)vt_lo;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    const long long adims[4] = {C, W, H, B};
+    const long long bdims[3] = {C, N, 1};
+    int rc, BN2 = 0;
+    if (tc_use_2cta() && tc2_applicable(B, H, W, N, 1, 0, N, &BN2)) {
+        const int bw = W >= 256 ? 128 : W, bh = W >= 256 ? 1 : 128 / W;
+        const int abox[4] = {64, bw, bh, 1};
+        const int bbox[3] = {64, BN2 / 2, 1};
+        if ((rc = make_map(&a_hi, x_hi, 4, adims, abox)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox)) ||
+            (rc = make_map(&b_hi, w_hi, 3, bdims, bbox)) || (rc = make_map(&b_lo, w_lo, 3, bdims, bbox)))
+            return rc;
+        return launch_tc2(BN2, a_hi, a_lo, b_hi, b_lo, p, B, H, W, N, (cudaStream_t)stream);
+    }
+    TilePlan t = plan_tiles(B, H, W, N, 0);
+    const int abox[4] = {t.BK, t.BW, t.BH, 1};
+    const int bbox[3] = {t.BK, t.BN, 1};
+    if ((rc = make_map(&a_hi, x_hi, 4, adims, abox)) || (rc = make_map(&a_lo, x_lo, 4, adims, abox)) ||
+        (rc = make_map(&b_hi, w_hi, 3, bdims, bbox)) || (rc = make_map(&b_lo, w_lo, 3, bdims, bbox)))
+        return rc;
+    p.tiles_x = cdiv(W, t.BW); p.tiles_y = cdiv(H, t.BH); p.BW = t.BW; p.BH = t.BH; p.kblocks_per_tap = C / t.BK;
+    return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, p.tiles_x * p.tiles_y * B, N, (cudaStream_t)stream);
+}
+
 // ---- Upsample (nearest x2 + 3x3 conv, diffusionmodules/model.py:49-52) in sub-pixel form ----------------------------
 // Output pixel (2i + py, 2j + px) only sees the 2 x 2 low-resolution neighbourhood rows {i - 1 + py, i + py} x columns
 // {j - 1 + px, j + px}; the nine taps collapse onto it with pre-summed weights (w_hi / w_lo: [4 parities][Cout][4 Cin],

@@ -146,6 +146,12 @@ struct TcParams {
     // (2 oy + py, 2 ox + px) of the 2Ho x 2Wo tensor; the GroupNorm partial sums of the four parity launches share one
     // buffer: stat_tiles slots per image (0 = this launch's own count), this launch's first slot = stat_tile0.
     int shift_x, shift_y, up, py, px, stat_tiles, stat_tile0;
+    // Fused q / k / v projection of an AttnBlock (diffusionmodules/model.py:158-175): one GEMM with N = 3C columns.  Columns
+    // below vt_col0 (q | k) go row-major to D_hi / D_lo with row pitch ldd (0 = N); columns from vt_col0 on (v) are stored
+    // TRANSPOSED as split bf16 V^T [b][column - vt_col0][vt_T tokens] -- the K-major B operand of the P.V product.
+    int ldd, vt_col0;
+    long long vt_T;
+    __nv_bfloat16 *vt_hi, *vt_lo;
 };
 
 // per-warp GroupNorm partial sums of one 32-column chunk: CPG channels per group, rows = lanes
@@ -186,7 +192,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
     const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
     const long long m = p.up ? (long long)(2 * oy + p.py) * (2 * p.Wo) + (2 * ox + p.px)      // sub-pixel scatter
                              : (long long)oy * p.Wo + ox;  // row within the batch slice
-    const long long row_off = (long long)b * p.d_batch_stride + m * p.N;
+    const long long row_off = (long long)b * p.d_batch_stride + m * (p.ldd ? p.ldd : p.N);
     const float bm = (p.bias_m && row_ok) ? __ldg(p.bias_m + m) : 0.0f;
     float *stg = es.tile[q];
     __syncwarp();
@@ -260,6 +266,41 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
                 const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.R + row_off + n + j));
                 o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
             }
+        }
+        if (p.vt_hi && n >= p.vt_col0) {              // v columns: transpose the 32 x 32 chunk through the staging tile
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(stg + lane * STG_STRIDE + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            __syncwarp();
+            float col[32];                            // this lane's channel (n + lane) at the warp's 32 tokens
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) col[rr] = stg[rr * STG_STRIDE + lane];
+            __syncwarp();
+            const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+            const long long m0 = __shfl_sync(0xffffffffu, m, 0);
+            const bool contiguous = (okmask == 0xffffffffu) && (__shfl_sync(0xffffffffu, m, 31) == m0 + 31) && ((m0 & 7) == 0);
+            const long long base = ((long long)b * (p.n_valid - p.vt_col0) + (n - p.vt_col0 + lane)) * p.vt_T;
+            if (contiguous) {                         // 32 consecutive tokens: 64 contiguous bytes per plane and lane
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) split2(col[j], col[j + 1], hi[j / 2], lo[j / 2]);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    *reinterpret_cast<uint4 *>(p.vt_hi + base + m0 + 2 * j) = make_uint4(hi[j], hi[j + 1], hi[j + 2], hi[j + 3]);
+                    *reinterpret_cast<uint4 *>(p.vt_lo + base + m0 + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                }
+            } else {
+#pragma unroll 1
+                for (int rr = 0; rr < 32; ++rr) {
+                    const long long mr = __shfl_sync(0xffffffffu, m, rr);
+                    if ((okmask >> rr) & 1u) {
+                        const __nv_bfloat16 h = __float2bfloat16_rn(col[rr]);
+                        p.vt_hi[base + mr] = h;
+                        p.vt_lo[base + mr] = __float2bfloat16_rn(col[rr] - __bfloat162float(h));
+                    }
+                }
+            }
+            continue;
         }
         if (p.stats) {                                // GroupNorm statistics of the finished output, per warp
             float *dst = &stat_s[q][(c0 / p.cpg) * 2];

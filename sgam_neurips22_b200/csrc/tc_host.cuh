@@ -22,8 +22,10 @@ inline EncodeTiledFn get_encode() {
     return fn;
 }
 
-// bf16 tensor [d3][d2][d1][d0] (d0 innermost, contiguous), box {b0, b1, b2, 1}, swizzle span = box[0] * 2 bytes, zero OOB fill
-inline int make_map(CUtensorMap *m, const void *base, int rank, const long long *dims, const int *box, const int *estride = nullptr) {
+// bf16 tensor [d3][d2][d1][d0] (d0 innermost, contiguous), box {b0, b1, b2, 1}, swizzle span = box[0] * 2 bytes, zero OOB fill;
+// pitch0: elements between consecutive d1 rows when the rows are slices of a wider tensor (0 = dims[0], dense)
+inline int make_map(CUtensorMap *m, const void *base, int rank, const long long *dims, const int *box, const int *estride = nullptr,
+                    long long pitch0 = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { sgam_set_error("cuTensorMapEncodeTiled is unavailable"); return SGAM_ERR_CUDA; }
     cuuint64_t gd[4], gs[3];
@@ -31,7 +33,7 @@ inline int make_map(CUtensorMap *m, const void *base, int rank, const long long 
     unsigned long long stride = 2;
     for (int i = 0; i < rank; ++i) {
         gd[i] = (cuuint64_t)dims[i]; bd[i] = (cuuint32_t)box[i]; es[i] = estride ? (cuuint32_t)estride[i] : 1;
-        stride *= (unsigned long long)dims[i];
+        stride *= (unsigned long long)((i == 0 && pitch0) ? pitch0 : dims[i]);
         if (i < rank - 1) gs[i] = stride;
     }
     const CUtensorMapSwizzle sw = (box[0] == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;

@@ -486,13 +486,20 @@ def attention_tc_supported(B, T, C):
 
 def attention_tc(q, k, vT, scale, kv_splits=None):
     """Fused softmax(q . k^T * scale) . v on tcgen05 (AttnBlock, diffusionmodules/model.py:168-192): the [B,T,T] scores
-    never leave the SM.  q, k = (hi, lo) [B,T,C]; vT = (hi, lo) [B,C,T]; returns o = (hi, lo) [B,T,C].  kv_splits: key
-    splits per query tile (None = the library's choice: 1 unless the batch is too small to fill the SM pairs)."""
+    never leave the SM.  q, k = (hi, lo) [B,T,C] -- contiguous, or the column halves of one [B,T,2C] tensor (qkv_tc);
+    vT = (hi, lo) [B,C,T]; returns o = (hi, lo) [B,T,C].  kv_splits: key splits per query tile (None = the library's
+    choice: 1 unless the batch is too small to fill the SM pairs)."""
     lib = _lib.load()
-    for n, t in (("q_hi", q[0]), ("q_lo", q[1]), ("k_hi", k[0]), ("k_lo", k[1]), ("vT_hi", vT[0]), ("vT_lo", vT[1])):
-        _chk(t, torch.bfloat16, n)
     B, T, C = q[0].shape
-    if tuple(k[0].shape) != (B, T, C) or tuple(vT[0].shape) != (B, C, T):
+    ld = q[0].stride(1)
+    for n, t in (("q_hi", q[0]), ("q_lo", q[1]), ("k_hi", k[0]), ("k_lo", k[1])):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.bfloat16):
+            raise RuntimeError(f"attention_tc: {n} must be a CUDA bf16 tensor")
+        if tuple(t.shape) != (B, T, C) or t.stride(2) != 1 or t.stride(1) != ld or t.stride(0) != T * ld or ld % 8 or t.data_ptr() % 16:
+            raise RuntimeError(f"attention_tc: {n} shape {tuple(t.shape)} strides {t.stride()} (rows must share one pitch, a multiple of 8)")
+    for n, t in (("vT_hi", vT[0]), ("vT_lo", vT[1])):
+        _chk(t, torch.bfloat16, n)
+    if tuple(vT[0].shape) != (B, C, T):
         raise RuntimeError(f"attention_tc: shapes q {tuple(q[0].shape)} k {tuple(k[0].shape)} vT {tuple(vT[0].shape)}")
     if kv_splits is None:
         kv_splits = lib.sgam_attention_tc_splits(B, T)
@@ -502,8 +509,33 @@ def attention_tc(q, k, vT, scale, kv_splits=None):
         ws = torch.empty(lib.sgam_attention_tc_workspace_bytes(B, T, kv_splits) // 4, device=q[0].device)
     _lib.check(lib.sgam_attention_tc(q[0].data_ptr(), q[1].data_ptr(), k[0].data_ptr(), k[1].data_ptr(), vT[0].data_ptr(),
                                      vT[1].data_ptr(), o[0].data_ptr(), o[1].data_ptr(), B, T, C, float(scale), int(kv_splits),
-                                     _ptr(ws), _stream()), "sgam_attention_tc")
+                                     _ptr(ws), 0 if ld == C else int(ld), _stream()), "sgam_attention_tc")
     return o
+
+
+def qkv_tc_supported(B, H, W, C):
+    return bool(_lib.load().sgam_qkv_tc_supported(B, H, W, C))
+
+
+def qkv_tc(xs, w, bias, nsplit=3):
+    """The q / k / v projections of an AttnBlock (diffusionmodules/model.py:158-175) as one tcgen05 GEMM.  xs = (hi, lo)
+    [B,H,W,C]; w = (hi, lo) [3C, C] (rows of q, k, v); bias [3C].  Returns q, k = (hi, lo) views [B,T,C] of one [B,T,2C]
+    tensor and vT = (hi, lo) [B,C,T]."""
+    lib = _lib.load()
+    x_hi, x_lo = xs
+    _chk(x_hi, torch.bfloat16, "x_hi"), _chk(x_lo, torch.bfloat16, "x_lo"), _chk(w[0], torch.bfloat16, "w_hi"), _chk(w[1], torch.bfloat16, "w_lo")
+    _chk(bias, name="bias")
+    B, H, W, C = x_hi.shape
+    if tuple(w[0].shape) != (3 * C, C) or bias.numel() != 3 * C:
+        raise RuntimeError(f"qkv_tc: weight {tuple(w[0].shape)} / bias {tuple(bias.shape)} for C = {C}")
+    T = H * W
+    qk = _bf16_pair((B, T, 2 * C), x_hi.device)
+    vT = _bf16_pair((B, C, T), x_hi.device)
+    _lib.check(lib.sgam_qkv_tc(x_hi.data_ptr(), x_lo.data_ptr(), w[0].data_ptr(), w[1].data_ptr(), bias.data_ptr(), qk[0].data_ptr(),
+                               qk[1].data_ptr(), vT[0].data_ptr(), vT[1].data_ptr(), B, H, W, C, int(nsplit), _stream()), "sgam_qkv_tc")
+    q = (qk[0][..., :C], qk[1][..., :C])
+    k = (qk[0][..., C:], qk[1][..., C:])
+    return q, k, vT
 
 
 def gn_head_conv(x, gamma, beta, w_t, bias):

@@ -34,6 +34,7 @@ class VQGANEngine:
         self.mode, self.nsplit = mode, nsplit
         import os
         self.fused_head = os.environ.get("SGAM_FUSED_HEAD", "1") != "0"
+        self.fused_qkv = os.environ.get("SGAM_FUSED_QKV", "1") != "0"
         self.subpixel = os.environ.get("SGAM_SUBPIXEL", "1") != "0"
         self.fused_stem = os.environ.get("SGAM_FUSED_STEM", "1") != "0"
         self.p = {}
@@ -66,6 +67,12 @@ class VQGANEngine:
             for k, v in p.items():
                 if k.endswith(".weight") and v.dim() == 2 and k != "quantize.embedding.weight" and v.shape[1] % 64 == 0:
                     self.wsplit[k[:-len(".weight")]] = ops.split_weight(v, pad_rows_to=32)
+            # AttnBlock projections: q | k | v weight rows stacked for the fused projection GEMM (ops.qkv_tc)
+            for k in list(p.keys()):
+                if k.endswith(".q.weight") and p[k].dim() == 2 and p[k].shape[1] % 128 == 0:
+                    base = k[:-len(".q.weight")]
+                    self.wsplit[base + ".qkv"] = ops.split_weight(torch.cat([p[base + ".q.weight"], p[base + ".k.weight"], p[base + ".v.weight"]], 0).contiguous())
+                    self.p[base + ".qkv.bias"] = torch.cat([p[base + ".q.bias"], p[base + ".k.bias"], p[base + ".v.bias"]], 0).contiguous()
             # Upsample convs (nearest x2 + 3x3) also in sub-pixel form: four 2x2 parity filters on the low-resolution tensor
             for k, v in p.items():
                 if k.endswith(".upsample.conv.weight") and v.dim() == 2 and v.shape[1] % (9 * 64) == 0:
@@ -133,13 +140,19 @@ class VQGANEngine:
         scale = float(int(C) ** (-0.5))
         if self.mode == "tc" and f"{name}.q" in self.wsplit and T % 8 == 0 and T % 32 == 0 and self.tc_ok(f"{name}.q", x.shape, 1):
             hs = self.norm_split(f"{name}.norm", x, False)
+            flat = lambda pair, shape: (pair[0].view(shape), pair[1].view(shape))
+            fused = self.use_fused_attention(B, T, C)
+            if fused and self.fused_qkv and f"{name}.qkv" in self.wsplit and ops.qkv_tc_supported(B, H, W, C):
+                # one GEMM for the three projections; q / k come back as the column halves of one tensor, V already transposed
+                q, k, vT = ops.qkv_tc(hs, self.wsplit[f"{name}.qkv"], self.p[f"{name}.qkv.bias"], nsplit=self.nsplit)
+                o = ops.attention_tc(q, k, vT, scale)
+                return self.conv_tc(f"{name}.proj_out", flat(o, (B, H, W, C)), 1, residual=x)
             q = self.conv_tc(f"{name}.q", hs, 1, out_f32=False, out_split=True)
             k = self.conv_tc(f"{name}.k", hs, 1, out_f32=False, out_split=True)
-            flat = lambda pair, shape: (pair[0].view(shape), pair[1].view(shape))
             # V^T [B, C, T] = W_v . h^T + b_v (bias per row), so that P.V is another A.B^T product
             vT = ops.gemm_nt_tc(self.wsplit[f"{name}.v"], flat(hs, (B, T, C)), bias_m=self.p[f"{name}.v.bias"],
                                 out_f32=False, out_split=True, nsplit=self.nsplit)
-            if self.use_fused_attention(B, T, C):
+            if fused:
                 # one flash-style kernel: scores / probabilities stay in tensor memory, [B,T,T] is never written
                 o = ops.attention_tc(flat(q, (B, T, C)), flat(k, (B, T, C)), vT, scale)
             else:

@@ -130,3 +130,50 @@ def test_unsupported_shapes_are_refused(ops):
     vt = ops.split_weight(torch.randn(1, 256, 384, device="cuda"))
     with pytest.raises(RuntimeError):
         ops.attention_tc(q, q, vt, 0.0625)
+
+
+# ---- fused q / k / v projection (sgam_qkv_tc): one GEMM, q | k row-major with a shared pitch, V stored transposed -------------
+# (B, H, W, C): pair kernel with 256-wide column tiles (8 x 64 x 64), 1-CTA kernel (1 x 64 x 64), 128-pixel rows (512^2 config),
+# the 512-channel mid block's width (not fused in the network, must still be right), W = 32
+@pytest.mark.parametrize("B,H,W,C", [(8, 64, 64, 256), (1, 64, 64, 256), (2, 128, 128, 256), (3, 32, 32, 512), (1, 8, 32, 128)])
+def test_fused_qkv_projection_matches_separate_ops(ops, B, H, W, C):
+    if not ops.qkv_tc_supported(B, H, W, C):
+        pytest.skip("shape not supported by the fused projection")
+    g = torch.Generator(device="cuda").manual_seed(C * 7 + H)
+    x = torch.randn(B, H, W, C, generator=g, device="cuda")
+    w = torch.randn(3 * C, C, generator=g, device="cuda") * C ** -0.5
+    bias = torch.randn(3 * C, generator=g, device="cuda")
+    xs = ops.split_bf16(x)
+    T = H * W
+    q, k, vT = ops.qkv_tc(xs, ops.split_weight(w), bias)
+    torch.cuda.synchronize()
+    assert q[0].shape == (B, T, C) and k[0].shape == (B, T, C) and vT[0].shape == (B, C, T)
+    # float64 reference of the three 1x1 convs (diffusionmodules/model.py:158-175)
+    ref = torch.einsum("btc,nc->btn", x.view(B, T, C).double(), w.double()) + bias.double()
+    got_q, got_k, got_v = q[0].float() + q[1].float(), k[0].float() + k[1].float(), (vT[0].float() + vT[1].float()).transpose(1, 2)
+    assert rel(got_q, ref[..., :C]) < 5e-5 and rel(got_k, ref[..., C:2 * C]) < 5e-5 and rel(got_v, ref[..., 2 * C:]) < 5e-5
+    # q, k: bit-identical to the separate launches they replace (same k-block order, same epilogue arithmetic); V^T: the separate
+    # launch computes W_v . h^T, i.e. with the operand roles -- and so the order of the hi*lo and lo*hi terms inside a k-block --
+    # exchanged: equal to fp32 accumulation-order noise
+    flat = (xs[0].view(B, T, C), xs[1].view(B, T, C))
+    for i, got in enumerate((q, k)):
+        wi = ops.split_weight(w[i * C:(i + 1) * C].contiguous())
+        sep = ops.conv2d_tc(xs, wi, bias[i * C:(i + 1) * C].contiguous(), ksize=1, cout=C, out_f32=False, out_split=True, gn_stats=False)
+        assert torch.equal(sep[0].view(B, T, C), got[0]) and torch.equal(sep[1].view(B, T, C), got[1])
+    sep_v = ops.gemm_nt_tc(ops.split_weight(w[2 * C:].contiguous()), flat, bias_m=bias[2 * C:].contiguous(), out_f32=False, out_split=True)
+    assert rel(vT[0].float() + vT[1].float(), sep_v[0].float() + sep_v[1].float()) < 1e-6
+
+
+def test_attention_reads_strided_q_and_k(ops):
+    """q and k as the column halves of one [B,T,2C] tensor (what qkv_tc returns) give the bits of the dense call."""
+    B, T, C = 2, 512, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qk = torch.randn(B, T, 2 * C, generator=g, device="cuda")
+    v = torch.randn(B, T, C, generator=g, device="cuda")
+    qs, ks = ops.split_weight(qk[..., :C].contiguous()), ops.split_weight(qk[..., C:].contiguous())
+    vts = ops.split_weight(v.transpose(1, 2).contiguous())
+    dense = ops.attention_tc(qs, ks, vts, C ** -0.5)
+    both = ops.split_weight(qk)
+    strided = ops.attention_tc((both[0][..., :C], both[1][..., :C]), (both[0][..., C:], both[1][..., C:]), vts, C ** -0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(dense[0], strided[0]) and torch.equal(dense[1], strided[1])
