@@ -349,6 +349,11 @@ class StepHarness:
             Bq, T, C = q.shape
             return 4.0 * Bq * T * T * C
 
+        def qkv_flops(a, kw, y):                   # three 1x1 convs C -> C of the same tensor
+            x = a[0][0]
+            C = x.shape[-1]
+            return 2.0 * (x.numel() // C) * 3 * C * C
+
         def timed(fn, flops_of):
             def wrapper(*a, **kw):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -362,7 +367,8 @@ class StepHarness:
             return wrapper
 
         patched = {"conv2d_tc": (ops.conv2d_tc, conv_flops), "gemm_nt_tc": (ops.gemm_nt_tc, gemm_flops),
-                   "attention_tc": (ops.attention_tc, attn_flops), "conv2d_tc_up2": (ops.conv2d_tc_up2, up2_flops)}
+                   "attention_tc": (ops.attention_tc, attn_flops), "conv2d_tc_up2": (ops.conv2d_tc_up2, up2_flops),
+                   "qkv_tc": (ops.qkv_tc, qkv_flops)}
         for name, (fn, fl) in patched.items():
             setattr(ops, name, timed(fn, fl))
         try:

@@ -264,16 +264,18 @@ int sgam_attention_tc(const void *q_hi, const void *q_lo, const void *k_hi, cons
  * 158-175) as ONE tcgen05 implicit GEMM with 3C output columns.  x [B,H,W,C] split bf16; w [3C, C] split bf16 = the rows of
  * q.weight, k.weight, v.weight; bias [3C] fp32.  qk [B, H*W, 2C] split bf16 (q = columns [0,C), k = [C,2C)); vt [B, C, H*W]
  * split bf16 = V^T, stored transposed by the epilogue (the K-major operand sgam_attention_tc / sgam_gemm_nt_tc expect).
- * Needs C % 128 == 0, W % 32 == 0, H*W % 128 == 0 and a shape sgam_tc_supported_conv accepts. */
+ * Needs C % 128 == 0, H*W % 8 == 0 and a shape sgam_tc_supported_conv accepts. */
 int sgam_qkv_tc_supported(int B, int H, int W, int C);
 int sgam_qkv_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias, void *qk_hi,
                 void *qk_lo, void *vt_hi, void *vt_lo, int B, int H, int W, int C, int nsplit, void *stream);
 
 /* Batched C = alpha * A . B^T (+ bias_m[row]) on tensor cores.  A [batch|1, M, K], B [batch|1, N, K] split-bf16
- * (a_batched / b_batched say whether the operand has the batch dimension); output fp32 C and/or split-bf16. */
+ * (a_batched / b_batched say whether the operand has the batch dimension); output fp32 C and/or split-bf16.
+ * lda / ldb: elements between consecutive rows of A / B (0 = K, dense) -- e.g. 2C for the q and k halves of sgam_qkv_tc's
+ * output; the batch slices are then M * lda (N * ldb) elements apart. */
 int sgam_gemm_nt_tc(const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo, const float *bias_m,
                     float *C, void *c_hi, void *c_lo, int batch, int M, int N, int K, int a_batched, int b_batched,
-                    float alpha, int nsplit, void *stream);
+                    float alpha, int nsplit, int lda, int ldb, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * RGB-D integration (use_rgbd_integration=True).  Replaces InfiniteSceneGeneration.rgbd_integration

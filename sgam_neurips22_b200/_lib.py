@@ -54,7 +54,7 @@ SIGNATURES = {
     "sgam_conv2d_tc_splitk_floats": (c_ll, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
     "sgam_tc_gn_partial_floats": (c_ll, [c_i, c_i, c_i]),
     "sgam_groupnorm_split_fused": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
-    "sgam_gemm_nt_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p]),
+    "sgam_gemm_nt_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_p]),
     "sgam_conv2d_tc_up2_supported": (c_i, [c_i, c_i, c_i, c_i, c_i]),
     "sgam_conv2d_tc_up2": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "sgam_stem_conv_in": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),

@@ -456,8 +456,9 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
 // v.weight; bias [3C].  qk [B, H*W, 2C] split bf16 (q = columns [0, C), k = [C, 2C): the attention kernel reads both with a
 // row pitch of 2C); vt [B, C, H*W] split bf16 = V^T, written transposed by the epilogue (tc_common.cuh).
 extern "C" int sgam_qkv_tc_supported(int B, int H, int W, int C) {
-    return B > 0 && H > 0 && W > 0 && C % 128 == 0 && W % 32 == 0 && ((long long)H * W) % 128 == 0 &&
-           sgam_tc_supported_conv(H, W, C, 3 * C, 1, 1);
+    // (the transposed V store is vectorised when a warp's 32 rows are 32 consecutive tokens -- W % 32 == 0 or a tile that spans
+    // whole image rows -- and falls back to 2-byte stores otherwise)
+    return B > 0 && H > 0 && W > 0 && C % 128 == 0 && ((long long)H * W) % 8 == 0 && sgam_tc_supported_conv(H, W, C, 3 * C, 1, 1);
 }
 
 extern "C" int sgam_qkv_tc(const void *x_hi, const void *x_lo, const void *w_hi, const void *w_lo, const float *bias, void *qk_hi,
@@ -568,8 +569,9 @@ extern "C" long long sgam_conv2d_tc_splitk_floats(int B, int H, int W, int Cin, 
 
 extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const void *b_hi_p, const void *b_lo_p, const float *bias_m,
                                float *C, void *c_hi, void *c_lo, int batch, int M, int N, int K, int a_batched, int b_batched,
-                               float alpha, int nsplit, void *stream) {
+                               float alpha, int nsplit, int lda, int ldb, void *stream) {
     SGAM_REQUIRE(a_hi_p && a_lo_p && b_hi_p && b_lo_p && (C || (c_hi && c_lo)), "gemm_nt_tc: null pointer");
+    SGAM_REQUIRE((lda == 0 || (lda >= K && lda % 8 == 0)) && (ldb == 0 || (ldb >= K && ldb % 8 == 0)), "gemm_nt_tc: lda / ldb must be 0 (dense) or multiples of 8 >= K");
     SGAM_REQUIRE(batch > 0 && M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 32 == 0, "gemm_nt_tc: needs K %% 8 == 0 and N %% 32 == 0 (M=%d N=%d K=%d)", M, N, K);
     SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "gemm_nt_tc: nsplit must be 1 or 3");
     int BN2 = 0;
@@ -580,8 +582,8 @@ extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const voi
         const long long bdims[3] = {K, N, b_batched ? batch : 1};
         const int bbox[3] = {64, BN2 / 2, 1};
         int rc;
-        if ((rc = make_map(&a_hi, a_hi_p, 4, adims, abox)) || (rc = make_map(&a_lo, a_lo_p, 4, adims, abox)) ||
-            (rc = make_map(&b_hi, b_hi_p, 3, bdims, bbox)) || (rc = make_map(&b_lo, b_lo_p, 3, bdims, bbox)))
+        if ((rc = make_map(&a_hi, a_hi_p, 4, adims, abox, nullptr, lda)) || (rc = make_map(&a_lo, a_lo_p, 4, adims, abox, nullptr, lda)) ||
+            (rc = make_map(&b_hi, b_hi_p, 3, bdims, bbox, nullptr, ldb)) || (rc = make_map(&b_lo, b_lo_p, 3, bdims, bbox, nullptr, ldb)))
             return rc;
         TcParams p{};
         p.Ho = 1; p.Wo = M; p.taps = 1; p.ks = 1; p.pad = 0; p.stride = 1; p.kblocks_per_tap = cdiv(K, 64);
@@ -599,8 +601,8 @@ extern "C" int sgam_gemm_nt_tc(const void *a_hi_p, const void *a_lo_p, const voi
     const long long bdims[3] = {K, N, b_batched ? batch : 1};
     const int bbox[3] = {t.BK, t.BN, 1};
     int rc;
-    if ((rc = make_map(&a_hi, a_hi_p, 4, adims, abox)) || (rc = make_map(&a_lo, a_lo_p, 4, adims, abox)) ||
-        (rc = make_map(&b_hi, b_hi_p, 3, bdims, bbox)) || (rc = make_map(&b_lo, b_lo_p, 3, bdims, bbox)))
+    if ((rc = make_map(&a_hi, a_hi_p, 4, adims, abox, nullptr, lda)) || (rc = make_map(&a_lo, a_lo_p, 4, adims, abox, nullptr, lda)) ||
+        (rc = make_map(&b_hi, b_hi_p, 3, bdims, bbox, nullptr, ldb)) || (rc = make_map(&b_lo, b_lo_p, 3, bdims, bbox, nullptr, ldb)))
         return rc;
     TcParams p{};
     p.tiles_x = cdiv(M, t.BW); p.tiles_y = 1; p.BW = t.BW; p.BH = 1; p.Ho = 1; p.Wo = M;

@@ -455,14 +455,26 @@ def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=
     return y if out_f32 else pair
 
 
+def _rows_pitch(t, name):
+    """Row pitch (elements) of a bf16 operand [batch, R, K] / [R, K] whose rows may be column slices of a wider tensor."""
+    if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.bfloat16):
+        raise RuntimeError(f"{name}: expected a CUDA bf16 tensor")
+    ld = t.stride(-2)
+    if t.stride(-1) != 1 or ld < t.shape[-1] or ld % 8 or t.data_ptr() % 16 or (t.dim() == 3 and t.shape[0] > 1 and t.stride(0) != t.shape[1] * ld):
+        raise RuntimeError(f"{name}: shape {tuple(t.shape)} strides {t.stride()} is not a row-pitched operand")
+    return int(ld)
+
+
 def gemm_nt_tc(a, b, bias_m=None, alpha=1.0, out_f32=True, out_split=False, nsplit=3):
     """C = alpha * A . B^T (+ bias_m per row) on tcgen05.  a = (hi, lo) [batch, M, K] or [M, K] (shared);
-    b = (hi, lo) [batch, N, K] or [N, K] (shared).  Output [batch, M, N]."""
+    b = (hi, lo) [batch, N, K] or [N, K] (shared); rows may be column slices of a wider tensor (one pitch per operand).
+    Output [batch, M, N]."""
     lib = _lib.load()
     a_hi, a_lo = a
     b_hi, b_lo = b
-    for n, t in (("a_hi", a_hi), ("a_lo", a_lo), ("b_hi", b_hi), ("b_lo", b_lo)):
-        _chk(t, torch.bfloat16, n)
+    lda, ldb = _rows_pitch(a_hi, "a_hi"), _rows_pitch(b_hi, "b_hi")
+    if _rows_pitch(a_lo, "a_lo") != lda or _rows_pitch(b_lo, "b_lo") != ldb:
+        raise RuntimeError("gemm_nt_tc: the hi and lo planes of an operand must share one row pitch")
     a_b, b_b = a_hi.dim() == 3, b_hi.dim() == 3
     batch = a_hi.shape[0] if a_b else (b_hi.shape[0] if b_b else 1)
     M, K = a_hi.shape[-2:]
@@ -474,7 +486,7 @@ def gemm_nt_tc(a, b, bias_m=None, alpha=1.0, out_f32=True, out_split=False, nspl
     pair = _bf16_pair((batch, M, N), dev) if out_split else (None, None)
     _lib.check(lib.sgam_gemm_nt_tc(a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), _ptr(bias_m),
                                    _ptr(y), _ptr(pair[0]), _ptr(pair[1]), batch, M, N, K, int(a_b), int(b_b), float(alpha),
-                                   nsplit, _stream()), "sgam_gemm_nt_tc")
+                                   nsplit, 0 if lda == K else lda, 0 if ldb == K else ldb, _stream()), "sgam_gemm_nt_tc")
     if out_f32 and out_split:
         return y, pair
     return y if out_f32 else pair

@@ -141,22 +141,20 @@ class VQGANEngine:
         if self.mode == "tc" and f"{name}.q" in self.wsplit and T % 8 == 0 and T % 32 == 0 and self.tc_ok(f"{name}.q", x.shape, 1):
             hs = self.norm_split(f"{name}.norm", x, False)
             flat = lambda pair, shape: (pair[0].view(shape), pair[1].view(shape))
-            fused = self.use_fused_attention(B, T, C)
-            if fused and self.fused_qkv and f"{name}.qkv" in self.wsplit and ops.qkv_tc_supported(B, H, W, C):
+            if self.fused_qkv and f"{name}.qkv" in self.wsplit and ops.qkv_tc_supported(B, H, W, C):
                 # one GEMM for the three projections; q / k come back as the column halves of one tensor, V already transposed
                 q, k, vT = ops.qkv_tc(hs, self.wsplit[f"{name}.qkv"], self.p[f"{name}.qkv.bias"], nsplit=self.nsplit)
-                o = ops.attention_tc(q, k, vT, scale)
-                return self.conv_tc(f"{name}.proj_out", flat(o, (B, H, W, C)), 1, residual=x)
-            q = self.conv_tc(f"{name}.q", hs, 1, out_f32=False, out_split=True)
-            k = self.conv_tc(f"{name}.k", hs, 1, out_f32=False, out_split=True)
-            # V^T [B, C, T] = W_v . h^T + b_v (bias per row), so that P.V is another A.B^T product
-            vT = ops.gemm_nt_tc(self.wsplit[f"{name}.v"], flat(hs, (B, T, C)), bias_m=self.p[f"{name}.v.bias"],
-                                out_f32=False, out_split=True, nsplit=self.nsplit)
-            if fused:
-                # one flash-style kernel: scores / probabilities stay in tensor memory, [B,T,T] is never written
-                o = ops.attention_tc(flat(q, (B, T, C)), flat(k, (B, T, C)), vT, scale)
             else:
-                s = ops.gemm_nt_tc(flat(q, (B, T, C)), flat(k, (B, T, C)), alpha=scale, nsplit=self.nsplit)    # [B, T, T] fp32
+                q = flat(self.conv_tc(f"{name}.q", hs, 1, out_f32=False, out_split=True), (B, T, C))
+                k = flat(self.conv_tc(f"{name}.k", hs, 1, out_f32=False, out_split=True), (B, T, C))
+                # V^T [B, C, T] = W_v . h^T + b_v (bias per row), so that P.V is another A.B^T product
+                vT = ops.gemm_nt_tc(self.wsplit[f"{name}.v"], flat(hs, (B, T, C)), bias_m=self.p[f"{name}.v.bias"],
+                                    out_f32=False, out_split=True, nsplit=self.nsplit)
+            if self.use_fused_attention(B, T, C):
+                # one flash-style kernel: scores / probabilities stay in tensor memory, [B,T,T] is never written
+                o = ops.attention_tc(q, k, vT, scale)
+            else:
+                s = ops.gemm_nt_tc(q, k, alpha=scale, nsplit=self.nsplit)                                       # [B, T, T] fp32
                 p = ops.softmax_split(s)
                 o = ops.gemm_nt_tc(p, vT, out_f32=False, out_split=True, nsplit=self.nsplit)                    # [B, T, C]
             return self.conv_tc(f"{name}.proj_out", flat(o, (B, H, W, C)), 1, residual=x)

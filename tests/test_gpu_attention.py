@@ -135,7 +135,8 @@ def test_unsupported_shapes_are_refused(ops):
 # ---- fused q / k / v projection (sgam_qkv_tc): one GEMM, q | k row-major with a shared pitch, V stored transposed -------------
 # (B, H, W, C): pair kernel with 256-wide column tiles (8 x 64 x 64), 1-CTA kernel (1 x 64 x 64), 128-pixel rows (512^2 config),
 # the 512-channel mid block's width (not fused in the network, must still be right), W = 32
-@pytest.mark.parametrize("B,H,W,C", [(8, 64, 64, 256), (1, 64, 64, 256), (2, 128, 128, 256), (3, 32, 32, 512), (1, 8, 32, 128)])
+@pytest.mark.parametrize("B,H,W,C", [(8, 64, 64, 256), (1, 64, 64, 256), (2, 128, 128, 256), (3, 32, 32, 512), (1, 8, 32, 128),
+                                     (8, 16, 16, 512), (1, 16, 16, 512), (2, 8, 8, 256)])
 def test_fused_qkv_projection_matches_separate_ops(ops, B, H, W, C):
     if not ops.qkv_tc_supported(B, H, W, C):
         pytest.skip("shape not supported by the fused projection")
@@ -177,3 +178,18 @@ def test_attention_reads_strided_q_and_k(ops):
     strided = ops.attention_tc((both[0][..., :C], both[1][..., :C]), (both[0][..., C:], both[1][..., C:]), vts, C ** -0.5)
     torch.cuda.synchronize()
     assert torch.equal(dense[0], strided[0]) and torch.equal(dense[1], strided[1])
+
+
+def test_gemm_nt_reads_row_pitched_operands(ops):
+    """The three-pass attention of the 512-channel blocks takes q and k straight from qkv_tc's [B,T,2C] tensor."""
+    B, T, C = 3, 256, 512
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qk = torch.randn(B, T, 2 * C, generator=g, device="cuda")
+    both = ops.split_weight(qk)
+    q, k = (both[0][..., :C], both[1][..., :C]), (both[0][..., C:], both[1][..., C:])
+    dense = ops.gemm_nt_tc((q[0].contiguous(), q[1].contiguous()), (k[0].contiguous(), k[1].contiguous()), alpha=C ** -0.5)
+    strided = ops.gemm_nt_tc(q, k, alpha=C ** -0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(dense, strided)
+    ref = torch.einsum("btc,bsc->bts", qk[..., :C].double(), qk[..., C:].double()) * C ** -0.5
+    assert rel(strided, ref) < 5e-5
