@@ -12,7 +12,7 @@
 //                  complete_tx of both CTAs' TMA loads (cp.async.bulk.tensor ... .cta_group::2 onto the leader's barrier).
 //   empty[s]       one per CTA; the leader's tcgen05.commit multicasts the arrival to both.
 //   tmem_full[a]   one per CTA; multicast commit after the last k-block of a tile.
-//   tmem_empty[a]  lives in the leader; 8 arrivals (4 epilogue warps x 2 CTAs, remote for r = 1).
+//   tmem_empty[a]  lives in the leader; 2 EW arrivals (EW = 4 or 8 epilogue warps x 2 CTAs, remote for r = 1).
 #include "tc_common.cuh"
 #include "tc_host.cuh"
 #include "tc_pair.cuh"
@@ -21,8 +21,9 @@ using namespace tc;
 
 namespace {
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW = 4>
 struct Tc2Cfg {
+    static constexpr int THREADS = 64 + 32 * EW;              // producer warp, MMA warp, EW epilogue warps
     static constexpr int A_PLANE = 128 * 128;                 // 128 rows x 64 bf16
     static constexpr int B_PLANE = (BN / 2) * 128;            // this CTA's half of the weight tile
     static constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;
@@ -37,19 +38,19 @@ struct Pair {                   // geometry of the 256-row pair tile
     int dx, dy;                 // offset of rank 1's 128-pixel box inside the pair tile
 };
 
-template <int BN, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+template <int BN, int STAGES, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                 const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams p, const Pair g) {
-    using Cfg = Tc2Cfg<BN, STAGES>;
+    using Cfg = Tc2Cfg<BN, STAGES, EW>;
     constexpr int A_PLANE = Cfg::A_PLANE, B_PLANE = Cfg::B_PLANE, STAGE_BYTES = Cfg::STAGE_BYTES, BK = 64;
     SGAM_PDL_TRIGGER();                              // the next kernel may start launching; it waits for our completion itself
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float stat_s[4][BN / 4 * 2];
-    __shared__ __align__(16) EpiStage epi_stage;      // per-warp transpose tiles of the coalesced epilogue stores
+    __shared__ float stat_s[EW][BN / 4 * 2];
+    __shared__ __align__(16) EpiStageT<EW> epi_stage; // per-warp transpose tiles of the coalesced epilogue stores
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -59,7 +60,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 2 * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -135,8 +136,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             }
         }
     } else {
-        // ===== epilogue (both CTAs): 128 rows of the pair tile each =====
-        const int q = warp & 3;
+        // ===== epilogue (both CTAs): 128 rows of the pair tile each; TMEM lane quadrant q = warp % 4, warp index w =====
+        const int q = warp & 3, w = EW == 4 ? q : warp - 2;
         int li = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++li) {
             const int acc = li & 1;
@@ -151,7 +152,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const long long per_img = p.stat_tiles ? p.stat_tiles : 2LL * g.tiles_x2 * g.tiles_y2;
             const long long slot = (long long)b * per_img + p.stat_tile0 + (long long)m2 * 2 + rank;
-            epilogue_rows<BN>(p, tmem_acc, q * 32 + lane, b, oy0, ox0, n0, n_tile, 0, slot, stat_s, epi_stage, q, lane);
+            epilogue_rows<BN, EW>(p, tmem_acc, q * 32 + lane, b, oy0, ox0, n0, n_tile, 0, slot, stat_s, epi_stage, w, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(map_to_cta(&tmem_empty_bar[acc], 0));
@@ -166,18 +167,18 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_consta
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW>
 int launch2_cfg(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo, const TcParams &p,
                 const Pair &g, cudaStream_t s) {
-    using Cfg = Tc2Cfg<BN, STAGES>;
+    using Cfg = Tc2Cfg<BN, STAGES, EW>;
     static bool configured = false;
     if (!configured) {
-        SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm2_kernel<BN, STAGES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         configured = true;
     }
     const int total = p.tiles_m * p.tiles_n, max_clusters = sm_count_cached() / 2;
     const int clusters = total < max_clusters ? total : max_clusters;
-    SGAM_PDL_LAUNCH(SGAM_PDL_GEMM2, (tc_gemm2_kernel<BN, STAGES>), 2 * clusters, TC_THREADS, Cfg::SMEM, s, a_hi, a_lo, b_hi, b_lo, p, g);
+    SGAM_PDL_LAUNCH(SGAM_PDL_GEMM2, (tc_gemm2_kernel<BN, STAGES, EW>), 2 * clusters, Cfg::THREADS, Cfg::SMEM, s, a_hi, a_lo, b_hi, b_lo, p, g);
     return SGAM_OK;
 }
 
@@ -211,8 +212,16 @@ int launch_tc2(int BN, const CUtensorMap &a_hi, const CUtensorMap &a_lo, const C
     p.tiles_m = g.tiles_x2 * g.tiles_y2 * B;
     p.tiles_n = N / BN;
     p.ksplit = 1; p.kb_per_split = p.taps * p.kblocks_per_tap;
-    if (BN == 256) return launch2_cfg<256, 3>(a_hi, a_lo, b_hi, b_lo, p, g, s);
-    return launch2_cfg<128, 4>(a_hi, a_lo, b_hi, b_lo, p, g, s);
+    // short K loops (1x1 convs, the fused q/k/v projection: <= 8 k-blocks) are bound by the epilogue: eight epilogue warps, and
+    // one ring stage less to make room for their staging tiles (SGAM_TC_EPI8=0: the four-warp kernels everywhere)
+    static int epi8 = -1;
+    if (epi8 < 0) { const char *e = getenv("SGAM_TC_EPI8"); epi8 = e ? atoi(e) : 1; }
+    if (epi8 && p.kb_per_split <= 8) {
+        if (BN == 256) return launch2_cfg<256, 2, 8>(a_hi, a_lo, b_hi, b_lo, p, g, s);
+        return launch2_cfg<128, 3, 8>(a_hi, a_lo, b_hi, b_lo, p, g, s);
+    }
+    if (BN == 256) return launch2_cfg<256, 3, 4>(a_hi, a_lo, b_hi, b_lo, p, g, s);
+    return launch2_cfg<128, 4, 4>(a_hi, a_lo, b_hi, b_lo, p, g, s);
 }
 
 }  // namespace tc

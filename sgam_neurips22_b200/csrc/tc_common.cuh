@@ -65,7 +65,8 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NTHREADS = 128>
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 in, fp32 accumulate), single CTA
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -172,10 +173,12 @@ __device__ __forceinline__ void chunk_group_sums(const float (&o)[32], bool row_
 // Per-warp staging for coalesced output stores: 32 rows x 32 fp32 columns, rows padded to 36 floats (16-byte aligned,
 // conflict-free for 128-bit accesses by quarter-warps), plus the global element offset of each of the warp's rows.
 constexpr int STG_STRIDE = 36;
-struct EpiStage {
-    float tile[4][32 * STG_STRIDE];
-    long long rowoff[4][32];                // row_off of row (32q + i), or -1 when the row is outside the image
+template <int EW>
+struct EpiStageT {
+    float tile[EW][32 * STG_STRIDE];
+    long long rowoff[EW][32];               // row_off of the warp's row i, or -1 when the row is outside the image
 };
+using EpiStage = EpiStageT<4>;
 
 // Epilogue of one 128-row accumulator: thread (q, lane) owns box row r (= TMEM lane 32q + lane) and walks the BN
 // columns in 32-wide chunks: VQ tile minimum, split-K partial store, or alpha / bias / residual + fp32 / split-bf16 /
@@ -184,9 +187,14 @@ struct EpiStage {
 // every warp-wide store touch 32 rows x 16 bytes (32 half-used sectors; the LSU, not HBM, then bounds the small-K
 // GEMMs).  The finished chunk therefore goes through the warp's staging tile and is written back row-contiguously:
 // 8 lanes x 16 B = one 128-byte line of a row (fp32), 4 lanes x 16 B = one 64-byte segment (bf16 planes).
-template <int BN>
+// EW epilogue warps (4 or 8): with 8, warps w and w + 4 share a TMEM lane quadrant (the same 32 rows) and take alternate 32-column
+// chunks -- a single warp per scheduler runs the ~400 dependent instructions of a chunk at a fraction of the issue rate, which
+// bounds the short-K (1x1) layers by their epilogue.  q below is the warp's index w in 0 .. EW-1 (staging tile, statistics slot).
+template <int BN, int EW = 4>
 __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_acc, int r, int b, int oy0, int ox0, int n0, int n_tile,
-                                      int ksp, long long slot, float (*stat_s)[BN / 4 * 2], EpiStage &es, int q, int lane) {
+                                      int ksp, long long slot, float (*stat_s)[BN / 4 * 2], EpiStageT<EW> &es, int q, int lane) {
+    constexpr int C_STEP = 32 * (EW / 4);
+    const int c_first = (q >> 2) * 32;
     const int ly = r / p.BW, lx = r - ly * p.BW;
     const int oy = oy0 + ly, ox = ox0 + lx;
     const bool row_ok = (oy < p.Ho) && (ox < p.Wo);
@@ -202,7 +210,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
         const float zz = row_ok ? __ldg(p.vq_zz + m) : 0.0f;                     // 32-code sub-tile (the refinement re-evaluates whole
         float *dst = p.vq_tilemin + (m * p.tiles_n + n_tile) * (BN / 32);        // sub-tiles: finer ones = fewer exact distances)
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
             uint32_t v[32];
             tmem_ld32(tmem_acc + (uint32_t)c0, v);
             float best = INFINITY;
@@ -219,7 +227,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
     if (p.ksplit > 1) {                               // raw partial sums; bias / residual / statistics happen in the reduce kernel
         float *dst = p.splitk_ws + (long long)ksp * p.split_stride + row_off + n0;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
             uint32_t v[32];
             tmem_ld32(tmem_acc + (uint32_t)c0, v);
             if (row_ok && n0 + c0 < p.n_valid) {
@@ -232,7 +240,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
         return;
     }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = c_first; c0 < BN; c0 += C_STEP) {
         uint32_t v[32];
         tmem_ld32(tmem_acc + (uint32_t)c0, v);
         const int n = n0 + c0;
@@ -290,8 +298,8 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
                     *reinterpret_cast<uint4 *>(p.vt_lo + base + m0 + 2 * j) = make_uint4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
                 }
             } else {
-#pragma unroll 1
-                for (int rr = 0; rr < 32; ++rr) {
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) {       // (unrolled: col[] must stay in registers)
                     const long long mr = __shfl_sync(0xffffffffu, m, rr);
                     if ((okmask >> rr) & 1u) {
                         const __nv_bfloat16 h = __float2bfloat16_rn(col[rr]);
@@ -348,15 +356,16 @@ __device__ __forceinline__ void epilogue_rows(const TcParams &p, uint32_t tmem_a
         }
     }
     if (p.stats) {
-        epilogue_bar_sync();
-        const int e = threadIdx.x - 64;                     // 0..127
+        epilogue_bar_sync<32 * EW>();
+        const int e = threadIdx.x - 64;                     // 0 .. 32 EW - 1
         const int nvals = (BN / p.cpg) * 2;
         if (e < nvals) {
-            const float v = (stat_s[0][e] + stat_s[1][e]) + (stat_s[2][e] + stat_s[3][e]);
+            const int h = (((e >> 1) * p.cpg) >> 5) % (EW / 4) * 4;       // the four warps that processed this group's chunk
+            const float v = (stat_s[h][e] + stat_s[h + 1][e]) + (stat_s[h + 2][e] + stat_s[h + 3][e]);
             const int g = n0 / p.cpg + (e >> 1);
-                                    p.stats[(slot * 32 + g) * 2 + (e & 1)] = v;
+            p.stats[(slot * 32 + g) * 2 + (e & 1)] = v;
         }
-        epilogue_bar_sync();
+        epilogue_bar_sync<32 * EW>();
     }
 }
 

@@ -27,6 +27,20 @@ qa, ka, va = (torch.randn(2, 512, 256, generator=g).cuda() for _ in range(3))
 oa = ops.attention_tc(ops.split_weight(qa), ops.split_weight(ka), ops.split_weight(va.transpose(1, 2).contiguous()), 256 ** -0.5)
 torch.cuda.synchronize()
 print("attn ok", float((oa[0].float() + oa[1].float()).double().sum()))
+# fused q / k / v projection: vectorised transposed V store (W = 64), 2-byte fallback (ragged last tile), strided q / k consumers
+for (Bq, Hq, Wq, Cq) in ((2, 64, 64, 256), (1, 8, 8, 128), (1, 24, 8, 128)):
+    xq = torch.randn(Bq, Hq, Wq, Cq, generator=g).cuda()
+    wq = (torch.randn(3 * Cq, Cq, generator=g) * Cq ** -0.5).cuda()
+    q_, k_, vT_ = ops.qkv_tc(ops.split_bf16(xq), ops.split_weight(wq), torch.randn(3 * Cq, generator=g).cuda())
+    s_ = ops.gemm_nt_tc(q_, k_, alpha=Cq ** -0.5)
+    torch.cuda.synchronize()
+    print("qkv ok", float(s_.double().sum()), float((vT_[0].float() + vT_[1].float()).double().sum()))
+oq = ops.attention_tc(q_, k_, vT_, 128 ** -0.5) if ops.attention_tc_supported(1, 192, 128) else None
+xq = torch.randn(2, 16, 16, 256, generator=g).cuda()
+q_, k_, vT_ = ops.qkv_tc(ops.split_bf16(xq), ops.split_weight((torch.randn(768, 256, generator=g) / 16).cuda()), torch.zeros(768, device="cuda"))
+oq = ops.attention_tc(q_, k_, vT_, 256 ** -0.5)
+torch.cuda.synchronize()
+print("qkv attn ok", float((oq[0].float() + oq[1].float()).double().sum()))
 for (Bu, Hu, Cu, Co) in ((3, 128, 128, 128), (5, 64, 256, 256)):
     xu = torch.randn(Bu, Hu, Hu, Cu, generator=g).cuda()
     wu = (torch.randn(Co, 9 * Cu, generator=g) * 0.03).cuda()
@@ -56,8 +70,8 @@ import hashlib
 print("step ok", float(decs[0][0].abs().mean()), hashlib.sha256(decs[0][0].cpu().numpy().tobytes()).hexdigest()[:16])
 PY
 echo "=== plain run (the sanitizer runs must reproduce this checksum) ==="
-python /tmp/san_step.py 2>&1 | grep -E "step ok|tsdf ok|swap ok|attn ok|up2 ok|stem/head ok"
+python /tmp/san_step.py 2>&1 | grep -E "step ok|tsdf ok|swap ok|attn ok|up2 ok|stem/head ok|qkv ok"
 for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
   echo "=== compute-sanitizer --tool $tool ==="
-  timeout -s KILL 900 compute-sanitizer --tool $tool python /tmp/san_step.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|step ok|tsdf ok|swap ok|attn ok|up2 ok|stem/head ok|Error|hazard" | head -14
+  timeout -s KILL 900 compute-sanitizer --tool $tool python /tmp/san_step.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|step ok|tsdf ok|swap ok|attn ok|up2 ok|stem/head ok|qkv ok|Error|hazard" | head -14
 done
