@@ -32,7 +32,9 @@ def test_split_producers(ops):
     hi, lo = ops.split_bf16(x.cuda(), upsample=1)
     up = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
     assert tuple(hi.shape) == (2, 12, 20, 128) and rel(hi.float() + lo.float(), up) < 2e-5
-    for C, hw in [(128, (12, 16)), (512, (4, 4))]:
+    # 384 / 640 channels: the grid stride is not a multiple of the channel-octet count (the kernel's per-element parameter path);
+    # (256, 96 x 96): more than one iteration per thread; (128, 7 x 9): a ragged tail
+    for C, hw in [(128, (12, 16)), (512, (4, 4)), (384, (10, 6)), (640, (3, 5)), (256, (96, 96)), (128, (7, 9))]:
         x = torch.randn(2, C, *hw, generator=g) * 2 + 3
         ga, be = torch.randn(C, generator=g), torch.randn(C, generator=g)
         for swish in (False, True):
