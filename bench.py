@@ -429,8 +429,8 @@ def e2e_record(serial_value, serial_ms, pf_value, pf_ms, h):
             "ms_per_step": best["ms_per_step"], "api": api, "mode": best["mode"], "serial": serial, "prefetch": prefetch}
 
 
-def measure(h, steps, warmup, world, prefetch=False):
-    """-> (value leg ms, e2e leg ms, e2e steps); prefetch=True adds the copy-stream variant: (.., prefetch leg ms)."""
+def measure(h, steps, warmup, world):
+    """-> (value leg ms, e2e leg ms, e2e steps)."""
     for _ in range(warmup):
         h.run()
     ms = time_steps(h.run, steps, world)
@@ -438,13 +438,7 @@ def measure(h, steps, warmup, world, prefetch=False):
         h.e2e()
     e2e_steps = max(3, min(steps, 20))
     ms_e2e = time_steps(h.e2e, e2e_steps, world)
-    if not prefetch:
-        return ms, ms_e2e, e2e_steps
-    h.e2e_prefetch_init()
-    for _ in range(warmup):
-        h.e2e_prefetch()
-    ms_pf = time_steps(h.e2e_prefetch, e2e_steps, world)
-    return ms, ms_e2e, e2e_steps, ms_pf
+    return ms, ms_e2e, e2e_steps
 
 
 def latest_traffic():
