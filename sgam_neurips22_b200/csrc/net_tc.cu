@@ -379,12 +379,13 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
     SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "conv2d_tc: nsplit must be 1 or 3");
     const int Npad = (Cout + 31) / 32 * 32;             // weight planes carry Npad rows (zero rows beyond Cout)
     SGAM_REQUIRE(!(out_nchw || Npad != Cout) || (y && !y_hi && !residual), "conv2d_tc: NCHW / ragged-Cout output is fp32 without residual");
-    if (swap_applicable(B, Ho, Wo, Cin, Cout, stride, y && !y_hi && !out_nchw && Npad == Cout)) {
+    if (swap_applicable(B, Ho, Wo, Cin, Cout, stride, !out_nchw && Npad == Cout)) {
         // 128 output channels on a full grid: channels on the M side, 256 pixels on the N side (net_tc3.cu)
         TcParams p{};
         p.Ho = Ho; p.Wo = Wo; p.taps = ksize * ksize; p.ks = ksize; p.pad = ksize / 2; p.stride = 1;
         p.N = Cout; p.n_valid = Cout; p.nsplit = nsplit; p.a_batched = 1; p.d_batch_stride = (long long)Ho * Wo * Cout; p.alpha = 1.0f;
-        p.bias_n = bias; p.R = residual; p.D = y; p.stats = gn_partial; p.cpg = Cout / 32;
+        p.bias_n = bias; p.R = residual; p.D = y; p.D_hi = (__nv_bfloat16 *)y_hi; p.D_lo = (__nv_bfloat16 *)y_lo;
+        p.stats = gn_partial; p.cpg = Cout / 32;
         return launch_conv_swap(x_hi, x_lo, w_hi, w_lo, p, B, H, W, Cin, Cout, ksize, (cudaStream_t)stream);
     }
     int BN2 = 0;

@@ -170,8 +170,18 @@ tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bn;
                 }
+                if (p.D) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) p.D[off + (long long)j * xstep] = o[j];     // lanes = 32 consecutive channels: one 128-byte line
+                    for (int j = 0; j < 32; ++j) p.D[off + (long long)j * xstep] = o[j]; // lanes = 32 consecutive channels: one 128-byte line
+                }
+                if (p.D_hi) {                       // split-bf16 planes for a consumer that is another tensor-core conv (Downsample /
+#pragma unroll                                      // sub-pixel Upsample): 64 contiguous bytes per plane and pixel
+                    for (int j = 0; j < 32; ++j) {
+                        const __nv_bfloat16 h = __float2bfloat16_rn(o[j]);
+                        p.D_hi[off + (long long)j * xstep] = h;
+                        p.D_lo[off + (long long)j * xstep] = __float2bfloat16_rn(o[j] - __bfloat162float(h));
+                    }
+                }
                 if (p.stats) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { s_acc += o[j]; q_acc = fmaf(o[j], o[j], q_acc); }

@@ -412,6 +412,11 @@ def tc_supported_conv(H, W, Cin, Cout, ksize, stride):
     return bool(_lib.load().sgam_tc_supported_conv(H, W, Cin, Cout, ksize, stride))
 
 
+def conv2d_tc_splitk_floats(B, H, W, Cin, Cout, ksize, stride=1):
+    """Workspace floats conv2d_tc would use for a split K loop at this shape (0 = the K loop is not split)."""
+    return int(_lib.load().sgam_conv2d_tc_splitk_floats(B, H, W, Cin, Cout, ksize, stride))
+
+
 def conv2d_tc(x, w, bias, residual=None, ksize=3, stride=1, cout=None, out_nchw=False, out_f32=True, out_split=False, nsplit=3,
               gn_stats=False):
     """Conv on tcgen05 (stride 1 symmetric pad, or stride 2 = Downsample).  x = (hi, lo) bf16 [B,H,W,Cin];

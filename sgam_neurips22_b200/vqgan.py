@@ -35,6 +35,7 @@ class VQGANEngine:
         import os
         self.fused_head = os.environ.get("SGAM_FUSED_HEAD", "1") != "0"
         self.fused_qkv = os.environ.get("SGAM_FUSED_QKV", "1") != "0"
+        self.emit_split = os.environ.get("SGAM_EMIT_SPLIT", "1") != "0"    # producers of Downsample / Upsample inputs write split bf16
         self.subpixel = os.environ.get("SGAM_SUBPIXEL", "1") != "0"
         self.fused_stem = os.environ.get("SGAM_FUSED_STEM", "1") != "0"
         self.p = {}
@@ -107,6 +108,12 @@ class VQGANEngine:
             return False
         return ops.tc_supported_conv(H // stride, W // stride, Cin, self.p[f"{name}.weight"].shape[0], ksize, stride)
 
+    def unsplit_k(self, name, x_shape, ksize):
+        """True when the library runs this conv without a split K loop (under-filled grids split K and reduce into an fp32
+        tensor; their output cannot come out of the epilogue as split bf16)."""
+        B, H, W, Cin = x_shape
+        return ops.conv2d_tc_splitk_floats(B, H, W, Cin, self.p[f"{name}.weight"].shape[0], ksize, 1) == 0
+
     def conv_tc(self, name, xs, ksize, **kw):
         """tcgen05 conv on a split-bf16 activation pair."""
         kw.setdefault("gn_stats", True)       # nearly every fp32 conv output feeds a GroupNorm: fuse its statistics
@@ -120,20 +127,24 @@ class VQGANEngine:
             return self.conv_tc(name, ops.split_bf16(x, upsample), ksize, residual=residual)
         return self.conv(name, x, ksize=ksize, upsample=upsample, residual=residual)
 
-    def norm_conv(self, norm_name, conv_name, x, residual=None):
-        """GroupNorm + swish + 3x3 conv (the ResnetBlock / norm_out pattern)."""
+    def norm_conv(self, norm_name, conv_name, x, residual=None, want_split=False):
+        """GroupNorm + swish + 3x3 conv (the ResnetBlock / norm_out pattern).  want_split: the only consumer is another
+        tensor-core conv (Downsample / sub-pixel Upsample): return the (hi, lo) bf16 planes straight from the epilogue instead
+        of an fp32 tensor that a separate pass would split (falls back to fp32 where the tensor-core path does not apply)."""
         if self.tc_ok(conv_name, x.shape, 3):
+            if want_split and self.unsplit_k(conv_name, x.shape, 3):
+                return self.conv_tc(conv_name, self.norm_split(norm_name, x, True), 3, residual=residual, out_f32=False, out_split=True)
             return self.conv_tc(conv_name, self.norm_split(norm_name, x, True), 3, residual=residual)
         return self.conv(conv_name, self.norm(norm_name, x, True), ksize=3, residual=residual)
 
-    def resnet_block(self, name, x):
+    def resnet_block(self, name, x, want_split=False):
         """model.py:78-137 with temb=None, dropout 0."""
         h = self.norm_conv(f"{name}.norm1", f"{name}.conv1", x)
         if self.has(f"{name}.nin_shortcut"):
             x = self.conv_from_f32(f"{name}.nin_shortcut", x, 1)
-        return self.norm_conv(f"{name}.norm2", f"{name}.conv2", h, residual=x)
+        return self.norm_conv(f"{name}.norm2", f"{name}.conv2", h, residual=x, want_split=want_split)
 
-    def attn_block(self, name, x):
+    def attn_block(self, name, x, want_split=False):
         """model.py:140-192: single-head spatial self-attention over H*W tokens."""
         B, H, W, C = x.shape
         T = H * W
@@ -157,6 +168,8 @@ class VQGANEngine:
                 s = ops.gemm_nt_tc(q, k, alpha=scale, nsplit=self.nsplit)                                       # [B, T, T] fp32
                 p = ops.softmax_split(s)
                 o = ops.gemm_nt_tc(p, vT, out_f32=False, out_split=True, nsplit=self.nsplit)                    # [B, T, C]
+            if want_split and self.unsplit_k(f"{name}.proj_out", x.shape, 1):
+                return self.conv_tc(f"{name}.proj_out", flat(o, (B, H, W, C)), 1, residual=x, out_f32=False, out_split=True)
             return self.conv_tc(f"{name}.proj_out", flat(o, (B, H, W, C)), 1, residual=x)
         h_ = self.norm(f"{name}.norm", x, False)
         q = self.conv(f"{name}.q", h_, ksize=1).view(B, T, C)
@@ -180,16 +193,22 @@ class VQGANEngine:
         dd = self.dd
         nres, nrb = len(dd["ch_mult"]), dd["num_res_blocks"]
         for l in range(nres):                                             # h = encoder.conv_in(stem(x)), see encode()
+            down = f"encoder.down.{l}.downsample.conv"
             for b in range(nrb):
-                h = self.resnet_block(f"encoder.down.{l}.block.{b}", h)
-                if self.has(f"encoder.down.{l}.attn.{b}.norm"):
-                    h = self.attn_block(f"encoder.down.{l}.attn.{b}", h)
+                # the level's last tensor feeds only the Downsample conv (diffusionmodules/model.py:418-423: no skip connections):
+                # its producer emits the split-bf16 operand directly
+                last = self.emit_split and b == nrb - 1 and l != nres - 1 and self.tc_ok(down, h.shape, 3, stride=2)
+                has_attn = self.has(f"encoder.down.{l}.attn.{b}.norm")
+                h = self.resnet_block(f"encoder.down.{l}.block.{b}", h, want_split=last and not has_attn)
+                if has_attn:
+                    h = self.attn_block(f"encoder.down.{l}.attn.{b}", h, want_split=last)
             if l != nres - 1:
-                name = f"encoder.down.{l}.downsample.conv"
-                if self.tc_ok(name, h.shape, 3, stride=2):
-                    h = self.conv_tc(name, ops.split_bf16(h), 3, stride=2)
+                if isinstance(h, tuple):
+                    h = self.conv_tc(down, h, 3, stride=2)
+                elif self.tc_ok(down, h.shape, 3, stride=2):
+                    h = self.conv_tc(down, ops.split_bf16(h), 3, stride=2)
                 else:
-                    h = self.conv(name, h, ksize=3, stride=2, pad_mode=1)
+                    h = self.conv(down, h, ksize=3, stride=2, pad_mode=1)
         h = self.resnet_block("encoder.mid.block_1", h)
         h = self.attn_block("encoder.mid.attn_1", h)
         h = self.resnet_block("encoder.mid.block_2", h)
@@ -203,12 +222,23 @@ class VQGANEngine:
         h = self.attn_block("decoder.mid.attn_1", h)
         h = self.resnet_block("decoder.mid.block_2", h)
         for l in reversed(range(nres)):
+            name = f"decoder.up.{l}.upsample.conv"
             for b in range(nrb + 1):
-                h = self.resnet_block(f"decoder.up.{l}.block.{b}", h)
-                if self.has(f"decoder.up.{l}.attn.{b}.norm"):
-                    h = self.attn_block(f"decoder.up.{l}.attn.{b}", h)
+                # the level's last tensor feeds only the Upsample conv (:527-533); in sub-pixel form that conv reads the
+                # LOW-resolution split operand, which the producer's epilogue can write directly
+                last = False
+                if self.emit_split and b == nrb and l != 0 and self.subpixel and f"{name}.subpixel" in self.wsplit:
+                    Bh, Hh, Wh, _ = h.shape
+                    cmid = self.p[f"decoder.up.{l}.block.{b}.conv2.weight"].shape[0]
+                    last = ops.conv2d_tc_up2_supported(Bh, Hh, Wh, cmid, self.p[f"{name}.weight"].shape[0])
+                has_attn = self.has(f"decoder.up.{l}.attn.{b}.norm")
+                h = self.resnet_block(f"decoder.up.{l}.block.{b}", h, want_split=last and not has_attn)
+                if has_attn:
+                    h = self.attn_block(f"decoder.up.{l}.attn.{b}", h, want_split=last)
             if l != 0:
-                name = f"decoder.up.{l}.upsample.conv"
+                if isinstance(h, tuple):
+                    h = ops.conv2d_tc_up2(h, self.wsplit[f"{name}.subpixel"], self.p[f"{name}.bias"], nsplit=self.nsplit)
+                    continue
                 Bh, Hh, Wh, Ch = h.shape
                 if self.subpixel and f"{name}.subpixel" in self.wsplit and \
                         ops.conv2d_tc_up2_supported(Bh, Hh, Wh, Ch, self.p[f"{name}.weight"].shape[0]):

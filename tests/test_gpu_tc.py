@@ -361,3 +361,23 @@ def test_fused_stem_conv_in(ops, shape):
     y0 = ops.stem_conv_in(x.cuda(), None, w1.view(4, 5).contiguous().cuda(), b1.cuda(), w3.permute(0, 2, 3, 1).reshape(128, 36).contiguous().cuda(), b3.cuda(), gn_stats=False)
     ref0 = F.conv2d(F.conv2d(torch.cat([x, torch.zeros(B, 1, H, W)], 1).double(), w1.double(), b1.double()), w3.double(), b3.double(), padding=1)
     assert rel(y0.permute(0, 3, 1, 2), ref0) < 2e-6 and not hasattr(y0, "gn_partial")
+
+
+@pytest.mark.parametrize("B,H,W,C,res", [(1, 256, 256, 128, True), (2, 128, 128, 128, False)])
+def test_swapped_kernel_emits_split_planes(ops, B, H, W, C, res):
+    """The 128-channel (swapped-operand) kernel writes the split-bf16 planes of its output from the epilogue -- what the level's
+    Downsample / sub-pixel Upsample conv reads -- bit-identical to splitting its fp32 output in a separate pass."""
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, H, W, C, generator=g).cuda()
+    w = ops.split_weight((torch.randn(C, 9 * C, generator=g) * 0.03).cuda(), pad_rows_to=32)
+    bias = torch.randn(C, generator=g).cuda()
+    r = x if res else None
+    xs = ops.split_bf16(x)
+    y = ops.conv2d_tc(xs, w, bias, residual=r, ksize=3, gn_stats=False)
+    y2, pair = ops.conv2d_tc(xs, w, bias, residual=r, ksize=3, out_f32=True, out_split=True, gn_stats=False)
+    only = ops.conv2d_tc(xs, w, bias, residual=r, ksize=3, out_f32=False, out_split=True, gn_stats=False)
+    ref = ops.split_bf16(y)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2)
+    for got in (pair, only):
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
