@@ -44,6 +44,66 @@ struct SwapGeom {
     int BW2, BH2, tiles_x2, tiles_y2, wide, tiles128_x, tiles128;
 };
 
+// Epilogue of one 128-channel x 256-pixel accumulator (shared by the two swapped-operand kernels): warp q owns TMEM lanes
+// 32q.. = output channels n0 + 32q + lane; the columns are the tile's pixels.
+__device__ __forceinline__ void swap_epilogue_tile(const TcParams &p, const SwapGeom &g, uint32_t tmem_acc, int q, int lane, int n0,
+                                                   int tx, int ty, int b) {
+    const int cpg = p.cpg;                                          // channels per GroupNorm group (4 for 128 channels)
+    const int c = n0 + 32 * q + lane;                       // this thread's output channel
+    const float bn = p.bias_n ? __ldg(p.bias_n + c) : 0.0f;
+    float s_acc = 0.f, q_acc = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_acc + (uint32_t)c0, v);
+        const int ly = c0 / g.BW2, lx = c0 - ly * g.BW2;    // BW2 % 32 == 0: the 32 pixels of a chunk share a row
+        const int oy = ty * g.BH2 + ly, ox = tx * g.BW2 + lx;
+        const long long m = p.up ? (long long)(2 * oy + p.py) * (2 * p.Wo) + (2 * ox + p.px) : (long long)oy * p.Wo + ox;
+        const long long off = (long long)b * p.d_batch_stride + m * p.N + c;
+        const long long xstep = p.up ? 2LL * p.N : (long long)p.N;     // neighbouring tile pixels: every other output pixel when up
+        float o[32];
+        if (p.R) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __ldg(p.R + off + (long long)j * xstep);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] += p.alpha * __uint_as_float(v[j]) + bn;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bn;
+        }
+        if (p.D) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) p.D[off + (long long)j * xstep] = o[j]; // lanes = 32 consecutive channels: one 128-byte line
+        }
+        if (p.D_hi) {                       // split-bf16 planes for a consumer that is another tensor-core conv (Downsample /
+#pragma unroll                                      // sub-pixel Upsample): 64 contiguous bytes per plane and pixel
+            for (int j = 0; j < 32; ++j) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(o[j]);
+                p.D_hi[off + (long long)j * xstep] = h;
+                p.D_lo[off + (long long)j * xstep] = __float2bfloat16_rn(o[j] - __bfloat162float(h));
+            }
+        }
+        if (p.stats) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s_acc += o[j]; q_acc = fmaf(o[j], o[j], q_acc); }
+            if ((c0 & 127) == 96) {                          // a 128-pixel block is complete
+                float s = s_acc, qq = q_acc;
+                for (int d = 1; d < cpg; d <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); qq += __shfl_xor_sync(0xffffffffu, qq, d); }
+                if ((lane & (cpg - 1)) == 0) {
+                    const int half = c0 >> 7;
+                    const int tx128 = g.wide ? 2 * tx + half : tx, ty128 = g.wide ? ty : 2 * ty + half;
+                    const long long per_img = p.stat_tiles ? p.stat_tiles : g.tiles128;
+                    const long long slot = (long long)b * per_img + p.stat_tile0 + (long long)ty128 * g.tiles128_x + tx128;
+                    const int grp = c / cpg;
+                    p.stats[(slot * 32 + grp) * 2] = s;
+                    p.stats[(slot * 32 + grp) * 2 + 1] = qq;
+                }
+                s_acc = 0.f; q_acc = 0.f;
+            }
+        }
+    }
+}
+
 template <int BK, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_constant__ CUtensorMap mapP_lo,
@@ -137,7 +197,6 @@ tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_co
     } else {
         // ===== epilogue: warp q owns TMEM lanes 32q.. = output channels n0 + 32q + lane; columns are the box's pixels =====
         const int q = warp & 3;
-        const int cpg = p.cpg;                                      // channels per GroupNorm group (4 for 128 channels)
         int li = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
             const int acc = li & 1;
@@ -145,62 +204,10 @@ tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_co
             int t = tile / p.tiles_n;
             const int tx = t % g.tiles_x2; t /= g.tiles_x2;
             const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
-            const int c = n0 + 32 * q + lane;                       // this thread's output channel
-            const float bn = p.bias_n ? __ldg(p.bias_n + c) : 0.0f;
             mbar_wait(&tmem_full_bar[acc], (li >> 1) & 1);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-            float s_acc = 0.f, q_acc = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_acc + (uint32_t)c0, v);
-                const int ly = c0 / g.BW2, lx = c0 - ly * g.BW2;    // BW2 % 32 == 0: the 32 pixels of a chunk share a row
-                const int oy = ty * g.BH2 + ly, ox = tx * g.BW2 + lx;
-                const long long m = p.up ? (long long)(2 * oy + p.py) * (2 * p.Wo) + (2 * ox + p.px) : (long long)oy * p.Wo + ox;
-                const long long off = (long long)b * p.d_batch_stride + m * p.N + c;
-                const long long xstep = p.up ? 2LL * p.N : (long long)p.N;     // neighbouring tile pixels: every other output pixel when up
-                float o[32];
-                if (p.R) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = __ldg(p.R + off + (long long)j * xstep);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] += p.alpha * __uint_as_float(v[j]) + bn;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = p.alpha * __uint_as_float(v[j]) + bn;
-                }
-                if (p.D) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) p.D[off + (long long)j * xstep] = o[j]; // lanes = 32 consecutive channels: one 128-byte line
-                }
-                if (p.D_hi) {                       // split-bf16 planes for a consumer that is another tensor-core conv (Downsample /
-#pragma unroll                                      // sub-pixel Upsample): 64 contiguous bytes per plane and pixel
-                    for (int j = 0; j < 32; ++j) {
-                        const __nv_bfloat16 h = __float2bfloat16_rn(o[j]);
-                        p.D_hi[off + (long long)j * xstep] = h;
-                        p.D_lo[off + (long long)j * xstep] = __float2bfloat16_rn(o[j] - __bfloat162float(h));
-                    }
-                }
-                if (p.stats) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { s_acc += o[j]; q_acc = fmaf(o[j], o[j], q_acc); }
-                    if ((c0 & 127) == 96) {                          // a 128-pixel block is complete
-                        float s = s_acc, qq = q_acc;
-                        for (int d = 1; d < cpg; d <<= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); qq += __shfl_xor_sync(0xffffffffu, qq, d); }
-                        if ((lane & (cpg - 1)) == 0) {
-                            const int half = c0 >> 7;
-                            const int tx128 = g.wide ? 2 * tx + half : tx, ty128 = g.wide ? ty : 2 * ty + half;
-                            const long long per_img = p.stat_tiles ? p.stat_tiles : g.tiles128;
-                            const long long slot = (long long)b * per_img + p.stat_tile0 + (long long)ty128 * g.tiles128_x + tx128;
-                            const int grp = c / cpg;
-                            p.stats[(slot * 32 + grp) * 2] = s;
-                            p.stats[(slot * 32 + grp) * 2 + 1] = qq;
-                        }
-                        s_acc = 0.f; q_acc = 0.f;
-                    }
-                }
-            }
+            swap_epilogue_tile(p, g, tmem_acc, q, lane, n0, tx, ty, b);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -211,6 +218,207 @@ tc_gemm_swap_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_co
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
     }
+}
+
+// ---- 3x3 convolutions, one pixel-row load for the three horizontal taps ---------------------------------------------------
+// ncu on the kernel above (128 -> 128 channels at 256 x 256, 36 % of the step): 3.9 GB cross the L2 -> SM crossbar per launch at
+// 11.8 TB/s -- the chip-wide L2 throughput cap -- while the tensor pipe is 81 % busy: the layer is bound by operand traffic, and
+// two thirds of it are the nine tap-shifted copies of the SAME pixels.  The three taps of one filter row read one image row shifted
+// by one pixel, i.e. by one 128-byte row of the K-major operand, and a SWIZZLE_128B UMMA descriptor may start at ANY 128-byte row
+// (the swizzle is a function of the absolute shared-memory address; tools/probes/umma_shift_probe.cu: exact for shifts 0..7 with
+// the descriptor's base-offset field left 0).  So this kernel loads, per filter row kh and 64-channel chunk, the tile's pixel row
+// with a one-pixel halo on each side ONCE ((BWT + 2) x 64 channels, a 256-pixel box + a 2-pixel box; TMA's zero fill is the
+// padding) and issues the MMAs of kw = 0, 1, 2 with the B descriptor advanced by kw rows; only the 32 KB weight tiles stream per
+// tap.  Per 256-pixel tile: 6 x 66 KB of pixels + 18 x 32 KB of weights = 0.97 MB instead of 1.73 MB.
+// RPT image rows per tile: 1 (W % 256 == 0) or 2 (W == 128: two N = 128 MMAs per step, one per image row).
+template <int RPT>
+struct RowCfg {
+    static constexpr int BWT = 256 / RPT;                                          // tile pixels per image row
+    static constexpr int ROW_PLANE = ((BWT + 2) * 128 + 1023) / 1024 * 1024;       // one image row + halo, one plane (hi or lo)
+    static constexpr int P_PLANE = RPT * ROW_PLANE;
+    static constexpr int P_STAGE = 2 * P_PLANE;
+    static constexpr int W_PLANE = 128 * 128;                                      // 128 output channels x 64 input channels
+    static constexpr int W_STAGE = 2 * W_PLANE;
+    static constexpr int PS = 2, WS = 2;                                           // ring depths (pixel rows, weight tiles)
+    static constexpr uint32_t P_TX = 2u * RPT * (BWT + 2) * 128;                   // bytes TMA delivers per pixel stage (hi + lo)
+    static constexpr size_t SMEM = (size_t)PS * P_STAGE + (size_t)WS * W_STAGE + 1024;
+    static_assert(SMEM <= 227 * 1024, "rings exceed shared memory");
+};
+
+template <int RPT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_swaprow_kernel(const __grid_constant__ CUtensorMap mapP_hi, const __grid_constant__ CUtensorMap mapP_lo,
+                       const __grid_constant__ CUtensorMap mapT_hi, const __grid_constant__ CUtensorMap mapT_lo,
+                       const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo, const TcParams p,
+                       const SwapGeom g, const int Cin) {
+    using Cfg = RowCfg<RPT>;
+    constexpr int BWT = Cfg::BWT, ROW_PLANE = Cfg::ROW_PLANE, P_PLANE = Cfg::P_PLANE, P_STAGE = Cfg::P_STAGE;
+    constexpr int W_PLANE = Cfg::W_PLANE, W_STAGE = Cfg::W_STAGE, PS = Cfg::PS, WS = Cfg::WS;
+    SGAM_PDL_TRIGGER();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *p_ring = smem, *w_ring = smem + (size_t)PS * P_STAGE;
+    __shared__ __align__(8) uint64_t p_full[PS], p_empty[PS], w_full[WS], w_empty[WS], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KC = Cin / 64;                                    // 64-channel chunks
+    const int total_tiles = p.tiles_m * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PS; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
+        for (int s = 0; s < WS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    SGAM_PDL_WAIT();
+
+    if (warp == 0) {
+        // ===== TMA producer: one pixel stage per (filter row, channel chunk), three weight stages behind it =====
+        if (lane == 0) {
+            const bool three = p.nsplit == 3;
+            int pc = 0, wc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.tiles_n) * 128;
+                int t = tile / p.tiles_n;
+                const int tx = t % g.tiles_x2; t /= g.tiles_x2;
+                const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
+                const int cx = tx * BWT - 1;
+                for (int kh = 0; kh < 3; ++kh) {
+                    for (int kc = 0; kc < KC; ++kc, ++pc) {
+                        const int ps = pc % PS;
+                        mbar_wait(&p_empty[ps], ((pc / PS) & 1) ^ 1);
+                        uint8_t *pst = p_ring + (size_t)ps * P_STAGE;
+                        mbar_expect_tx(&p_full[ps], three ? Cfg::P_TX : Cfg::P_TX / 2);
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) {
+                            const int cy = ty * RPT + r + kh - 1;
+                            uint8_t *row = pst + r * ROW_PLANE;
+                            tma_load_4d(row, &mapP_hi, &p_full[ps], kc * 64, cx, cy, b);
+                            tma_load_4d(row + BWT * 128, &mapT_hi, &p_full[ps], kc * 64, cx + BWT, cy, b);
+                            if (three) {
+                                tma_load_4d(row + P_PLANE, &mapP_lo, &p_full[ps], kc * 64, cx, cy, b);
+                                tma_load_4d(row + P_PLANE + BWT * 128, &mapT_lo, &p_full[ps], kc * 64, cx + BWT, cy, b);
+                            }
+                        }
+                        for (int kw = 0; kw < 3; ++kw, ++wc) {
+                            const int ws = wc % WS;
+                            mbar_wait(&w_empty[ws], ((wc / WS) & 1) ^ 1);
+                            uint8_t *wst = w_ring + (size_t)ws * W_STAGE;
+                            const int kcol = (kh * 3 + kw) * Cin + kc * 64;
+                            mbar_expect_tx(&w_full[ws], three ? W_STAGE : W_PLANE);
+                            tma_load_3d(wst, &mapW_hi, &w_full[ws], kcol, n0, 0);
+                            if (three) tma_load_3d(wst + W_PLANE, &mapW_lo, &w_full[ws], kcol, n0, 0);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D^T (128 channels x BWT pixels per image row) += W (128 x 16) . P^T (16 x BWT), P advanced by kw rows =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BWT);
+            const bool three = p.nsplit == 3;
+            int pc = 0, wc = 0, li = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+                const int acc = li & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((li >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kh = 0; kh < 3; ++kh) {
+                    for (int kc = 0; kc < KC; ++kc, ++pc) {
+                        const int ps = pc % PS;
+                        mbar_wait(&p_full[ps], (pc / PS) & 1);
+                        tc_fence_after();
+                        const uint8_t *pst = p_ring + (size_t)ps * P_STAGE;
+                        for (int kw = 0; kw < 3; ++kw, ++wc) {
+                            const int ws = wc % WS;
+                            mbar_wait(&w_full[ws], (wc / WS) & 1);
+                            tc_fence_after();
+                            const uint8_t *wst = w_ring + (size_t)ws * W_STAGE;
+                            const uint64_t w_hi = make_smem_desc<128>(wst), w_lo = make_smem_desc<128>(wst + W_PLANE);
+                            const uint32_t fresh = (kh | kc | kw) ? 1u : 0u;
+#pragma unroll
+                            for (int r = 0; r < RPT; ++r) {
+                                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256 + r * BWT);
+                                const uint64_t a_hi = make_smem_desc<128>(pst + r * ROW_PLANE + kw * 128);
+                                const uint64_t a_lo = make_smem_desc<128>(pst + P_PLANE + r * ROW_PLANE + kw * 128);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t off = (uint64_t)(k * 2);
+                                    umma_bf16(tmem_d, w_hi + off, a_hi + off, idesc, (fresh | (uint32_t)k) ? 1u : 0u);
+                                    if (three) {
+                                        umma_bf16(tmem_d, w_hi + off, a_lo + off, idesc, 1u);
+                                        umma_bf16(tmem_d, w_lo + off, a_hi + off, idesc, 1u);
+                                    }
+                                }
+                            }
+                            umma_commit(&w_empty[ws]);
+                        }
+                        umma_commit(&p_empty[ps]);
+                    }
+                }
+                umma_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int li = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+            const int acc = li & 1;
+            const int n0 = (tile % p.tiles_n) * 128;
+            int t = tile / p.tiles_n;
+            const int tx = t % g.tiles_x2; t /= g.tiles_x2;
+            const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
+            mbar_wait(&tmem_full_bar[acc], (li >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+            swap_epilogue_tile(p, g, tmem_acc, q, lane, n0, tx, ty, b);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+int swaprow_mode() {           // SGAM_TC_SWAPROW=0: every swapped-operand conv on tc_gemm_swap_kernel (nine pixel boxes per chunk)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SGAM_TC_SWAPROW"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
+template <int RPT>
+int launch_swaprow(const void *x_hi, const void *x_lo, const CUtensorMap &w_hi, const CUtensorMap &w_lo, const TcParams &p, const SwapGeom &g,
+                   int B, int H, int W, int Cin, cudaStream_t s) {
+    using Cfg = RowCfg<RPT>;
+    CUtensorMap p_hi, p_lo, t_hi, t_lo;
+    const long long adims[4] = {Cin, W, H, B};
+    const int abox[4] = {64, Cfg::BWT, 1, 1}, tbox[4] = {64, 2, 1, 1};
+    int rc;
+    if ((rc = make_map(&p_hi, x_hi, 4, adims, abox)) || (rc = make_map(&p_lo, x_lo, 4, adims, abox)) ||
+        (rc = make_map(&t_hi, x_hi, 4, adims, tbox)) || (rc = make_map(&t_lo, x_lo, 4, adims, tbox)))
+        return rc;
+    static bool configured = false;
+    if (!configured) {
+        SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_swaprow_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured = true;
+    }
+    const int total = p.tiles_m * p.tiles_n;
+    const int grid = total < sm_count_cached() ? total : sm_count_cached();
+    SGAM_PDL_LAUNCH(SGAM_PDL_GEMM1, tc_gemm_swaprow_kernel<RPT>, grid, TC_THREADS, Cfg::SMEM, s, p_hi, p_lo, t_hi, t_lo, w_hi, w_lo, p, g, Cin);
+    return SGAM_OK;
 }
 
 int swap_mode() {              // 0 = off, 64 = BK 64 / 2 stages, 32 = BK 32 / 4 stages (SGAM_TC_SWAP)
@@ -269,6 +477,14 @@ int launch_conv_swap(const void *x_hi, const void *x_lo, const void *w_hi, const
     p.tiles_m = g.tiles_x2 * g.tiles_y2 * B;
     p.tiles_n = Cout / 128;
     p.ksplit = 1;
+    // plain 3x3 convolutions: one pixel-row load for the three horizontal taps (the sub-pixel Upsample's 2x2 parity convs stay here)
+    if (ksize == 3 && !p.up && p.shift_x == 0 && p.shift_y == 0 && swaprow_mode() && (W % 256 == 0 || W == 128)) {
+        CUtensorMap w64_hi, w64_lo;
+        const int wbox[3] = {64, 128, 1};
+        if ((rc = make_map(&w64_hi, w_hi, 3, bdims, wbox)) || (rc = make_map(&w64_lo, w_lo, 3, bdims, wbox))) return rc;
+        if (W == 128) return launch_swaprow<2>(x_hi, x_lo, w64_hi, w64_lo, p, g, B, H, W, Cin, s);
+        return launch_swaprow<1>(x_hi, x_lo, w64_hi, w64_lo, p, g, B, H, W, Cin, s);
+    }
     if (BK == 32) return launch_swap<32, 4>(p_hi, p_lo, wm_hi, wm_lo, p, g, s);
     return launch_swap<64, 2>(p_hi, p_lo, wm_hi, wm_lo, p, g, s);
 }

@@ -68,8 +68,11 @@ def test_gemm_nt_tc(ops, shape):
     assert 1e-4 < rel(y1, A.double() @ B.double().transpose(1, 2)) < 2e-2
 
 
+# the last two: the row-reuse kernel (net_tc3.cu) with two tiles per image row (interior halo pixels are real neighbours, the
+# right one of the last tile is padding) and with four channel chunks on two-row tiles (the pixel ring wraps inside a filter row)
 CONV_TC = [(1, 16, 16, 128, 128, 3), (2, 32, 32, 128, 256, 3), (1, 64, 64, 256, 256, 1), (1, 4, 4, 512, 512, 3),
-           (1, 256, 256, 128, 128, 3), (1, 8, 8, 256, 32, 1), (3, 128, 128, 128, 128, 3), (1, 2, 2, 512, 256, 3)]
+           (1, 256, 256, 128, 128, 3), (1, 8, 8, 256, 32, 1), (3, 128, 128, 128, 128, 3), (1, 2, 2, 512, 256, 3),
+           (1, 128, 512, 128, 128, 3), (3, 128, 128, 256, 128, 3)]
 
 
 @pytest.mark.parametrize("case", CONV_TC)
