@@ -364,13 +364,18 @@ class StepHarness:
             C = x.shape[-1]
             return 2.0 * (x.numel() // C) * 3 * C * C
 
+        def gnconv_flops(a, kw, y):                # GroupNorm + swish + 3x3 conv in one kernel: the conv's flops
+            x, w = a[0], a[3][0]
+            return 2.0 * (x.numel() // x.shape[-1]) * w.shape[0] * w.shape[1]
+
         def timed(fn, flops_of):
             def wrapper(*a, **kw):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 y = fn(*a, **kw)
                 e1.record()
-                shp = tuple(a[0][0].shape) + tuple((a[1][0] if isinstance(a[1], tuple) else a[1]).shape)
+                a0 = a[0][0] if isinstance(a[0], tuple) else a[0]
+                shp = tuple(a0.shape) + tuple((a[1][0] if isinstance(a[1], tuple) else a[1]).shape)
                 events.append((e0, e1, flops_of(a, kw, y), fn.__name__, shp,
                                {k: v for k, v in kw.items() if isinstance(v, (int, float, bool))}, tensor_bytes(a, kw, y)))
                 return y
@@ -378,7 +383,7 @@ class StepHarness:
 
         patched = {"conv2d_tc": (ops.conv2d_tc, conv_flops), "gemm_nt_tc": (ops.gemm_nt_tc, gemm_flops),
                    "attention_tc": (ops.attention_tc, attn_flops), "conv2d_tc_up2": (ops.conv2d_tc_up2, up2_flops),
-                   "qkv_tc": (ops.qkv_tc, qkv_flops)}
+                   "qkv_tc": (ops.qkv_tc, qkv_flops), "gn_conv2d_tc": (ops.gn_conv2d_tc, gnconv_flops)}
         for name, (fn, fl) in patched.items():
             setattr(ops, name, timed(fn, fl))
         try:

@@ -260,6 +260,17 @@ int sgam_attention_tc(const void *q_hi, const void *q_lo, const void *k_hi, cons
                       const void *vt_lo, void *o_hi, void *o_lo, int B, int T, int C, float scale, int kv_splits,
                       void *workspace, int ld_qk, void *stream);
 
+/* GroupNorm(32, Cin, eps = 1e-6) + swish + 3x3 conv (the ResnetBlock pattern norm -> nonlinearity -> conv, diffusionmodules/
+ * model.py:117-131) as ONE tensor-core kernel for the 128-channel layers on wide images: the fp32 activation x [B,H,W,Cin] is
+ * normalised, activated and split into bf16 planes inside the conv's operand path (no separate apply pass, no split operand in
+ * HBM).  gn_partial_in: the per-pixel-block sums x's producer left (sgam_tc_gn_partial_floats(B,H,W) floats; the library
+ * finalises them into its tail); w [Cout, 9 Cin] split bf16; residual / y / (y_hi, y_lo) / gn_partial_out as sgam_conv2d_tc.
+ * Operand bits and results are identical to sgam_groupnorm_split_fused followed by sgam_conv2d_tc. */
+int sgam_gn_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout);
+int sgam_gn_conv2d_tc(const float *x, float *gn_partial_in, const float *gamma, const float *beta, const void *w_hi,
+                      const void *w_lo, const float *bias, const float *residual, float *y, void *y_hi, void *y_lo, int B, int H,
+                      int W, int Cin, int Cout, int nsplit, float *gn_partial_out, void *stream);
+
 /* The q, k and v projections of an AttnBlock (three 1x1 convs of the same GroupNorm output, diffusionmodules/model.py:
  * 158-175) as ONE tcgen05 implicit GEMM with 3C output columns.  x [B,H,W,C] split bf16; w [3C, C] split bf16 = the rows of
  * q.weight, k.weight, v.weight; bias [3C] fp32.  qk [B, H*W, 2C] split bf16 (q = columns [0,C), k = [C,2C)); vt [B, C, H*W]

@@ -63,6 +63,8 @@ SIGNATURES = {
     "sgam_attention_tc_splits": (c_i, [c_i, c_i]),
     "sgam_attention_tc_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "sgam_attention_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_i, c_p]),
+    "sgam_gn_conv2d_tc_supported": (c_i, [c_i, c_i, c_i, c_i, c_i]),
+    "sgam_gn_conv2d_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "sgam_qkv_tc_supported": (c_i, [c_i, c_i, c_i, c_i]),
     "sgam_qkv_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sgam_unproject_points": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),

@@ -452,6 +452,32 @@ extern "C" int sgam_conv2d_tc(const void *x_hi, const void *x_lo, const void *w_
     return launch_tc(t, a_hi, a_lo, b_hi, b_lo, p, tiles_m, Npad, (cudaStream_t)stream);
 }
 
+// ---- GroupNorm + swish + 3x3 conv with the normalisation inside the conv's operand path (net_tc3.cu) ------------------------------
+// x fp32 NHWC [B,H,W,Cin] with the partial sums of its producer (gn_partial_in, sgam_tc_gn_partial_floats(B,H,W) floats); w [Cout, 9 Cin]
+// split bf16; y fp32 and / or (y_hi, y_lo); gn_partial_out: statistics of y for the next GroupNorm, or NULL.
+int sgam_gn_finalize_launch(float *gn_partial, int B, int H, int W, int C, cudaStream_t s, float **meanrstd_out);
+
+extern "C" int sgam_gn_conv2d_tc_supported(int B, int H, int W, int Cin, int Cout) {
+    return B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % 128 == 0 && Cin <= 512 && gnconv_applicable(B, H, W, Cin, Cout);
+}
+
+extern "C" int sgam_gn_conv2d_tc(const float *x, float *gn_partial_in, const float *gamma, const float *beta, const void *w_hi,
+                                 const void *w_lo, const float *bias, const float *residual, float *y, void *y_hi, void *y_lo, int B, int H,
+                                 int W, int Cin, int Cout, int nsplit, float *gn_partial_out, void *stream) {
+    SGAM_REQUIRE(x && gn_partial_in && gamma && beta && w_hi && w_lo && (y || (y_hi && y_lo)), "gn_conv2d_tc: null pointer");
+    SGAM_REQUIRE(nsplit == 1 || nsplit == 3, "gn_conv2d_tc: nsplit must be 1 or 3");
+    SGAM_REQUIRE(sgam_gn_conv2d_tc_supported(B, H, W, Cin, Cout), "gn_conv2d_tc: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
+    SGAM_REQUIRE(!gn_partial_out || (Cout % 128 == 0 && Cout <= 512), "gn_conv2d_tc: fused output statistics need Cout in {128,256,384,512}");
+    float *meanrstd = nullptr;
+    if (int rc = sgam_gn_finalize_launch(gn_partial_in, B, H, W, Cin, (cudaStream_t)stream, &meanrstd)) return rc;
+    TcParams p{};
+    p.Ho = H; p.Wo = W; p.taps = 9; p.ks = 3; p.pad = 1; p.stride = 1;
+    p.N = Cout; p.n_valid = Cout; p.nsplit = nsplit; p.a_batched = 1; p.d_batch_stride = (long long)H * W * Cout; p.alpha = 1.0f;
+    p.bias_n = bias; p.R = residual; p.D = y; p.D_hi = (__nv_bfloat16 *)y_hi; p.D_lo = (__nv_bfloat16 *)y_lo;
+    p.stats = gn_partial_out; p.cpg = Cout / 32;
+    return launch_gnconv(x, meanrstd, gamma, beta, w_hi, w_lo, p, B, H, W, Cin, Cout, (cudaStream_t)stream);
+}
+
 // ---- AttnBlock q / k / v projections (three 1x1 convs of the same normalised tensor, diffusionmodules/model.py:158-175) as
 // ONE implicit GEMM with N = 3C: the operand is read once and one launch replaces three.  w [3C, C] = rows of q.weight, k.weight,
 // v.weight; bias [3C].  qk [B, H*W, 2C] split bf16 (q = columns [0, C), k = [C, 2C): the attention kernel reads both with a

@@ -421,6 +421,229 @@ int launch_swaprow(const void *x_hi, const void *x_lo, const CUtensorMap &w_hi, 
     return SGAM_OK;
 }
 
+// ---- GroupNorm + swish inside the operand path of the row-reuse kernel ---------------------------------------------------------
+// The separate GroupNorm-apply pass of a 128-channel 256 x 256 layer moves 537 MB through HBM (94 us) to produce the split-bf16
+// operand the conv then reads.  With one pixel-row load per filter row every input element enters shared memory only three times, so
+// the transform can live here: TMA lands the fp32 rows ((256 + 2) pixels x 64 channels = 66 KB, exactly the size of the hi + lo
+// planes), eight transform warps read them into registers, apply (x - mean) * rstd * gamma + beta, swish and the bf16 split -- the same
+// expressions as gn_apply_split_kernel, so the operand bits are identical -- and write the two K-major SWIZZLE_128B planes IN PLACE
+// (all reads of a stage finish before the first write: named barrier); pixels outside the image become exact zeros AFTER the
+// activation, as the conv's padding requires.  W % 256 == 0 (one image row per tile) only.
+// STATUS: correct (bit-identical to the two-kernel path, tests/test_gpu_tc.py) but SLOWER -- 531 us against 94 + 295 us at 8 x 256 x 256
+// (442 us with the arithmetic removed): the N = 256 MMAs already read 96 B/clk of operands from shared memory and TMA writes another
+// 36 B/clk; the transform's 29 B/clk of loads / stores push the sum past the SM's 128 B/clk, and with 66 KB stages only two fit, so
+// TMA -> transform -> MMA serialise per buffer.  Opt-in (SGAM_FUSED_GNCONV=1); profiles/r2_rejected_experiments.txt.
+constexpr int GNC_TRANSFORM_WARPS = 8;
+constexpr int GNC_THREADS = TC_THREADS + 32 * GNC_TRANSFORM_WARPS;
+
+struct GnOperand {
+    const float *meanrstd, *gamma, *beta;   // [B][32][2], [Cin], [Cin]
+    int cpg, H, W;                          // channels per group (Cin / 32, a multiple of 4); image extent
+    int probe;                              // development probe (SGAM_GNCONV_PROBE): 1 = no swish, 2 = no arithmetic at all
+};
+
+__global__ void __launch_bounds__(GNC_THREADS, 1)
+tc_gemm_gnconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapXT,
+                      const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo, const TcParams p,
+                      const SwapGeom g, const int Cin, const GnOperand gn) {
+    using Cfg = RowCfg<1>;
+    constexpr int BWT = 256, P_PLANE = Cfg::P_PLANE, P_STAGE = Cfg::P_STAGE, W_PLANE = Cfg::W_PLANE, W_STAGE = Cfg::W_STAGE;
+    constexpr int PS = Cfg::PS, WS = Cfg::WS;
+    constexpr uint32_t X_TX = (BWT + 2) * 64 * 4;               // fp32 bytes per pixel stage
+    static_assert(X_TX <= P_STAGE, "the fp32 rows must fit the stage they are transformed in");
+    SGAM_PDL_TRIGGER();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *p_ring = smem, *w_ring = smem + (size_t)PS * P_STAGE;
+    __shared__ __align__(8) uint64_t x_full[PS], p_ready[PS], p_empty[PS], w_full[WS], w_empty[WS], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KC = Cin / 64;
+    const int total_tiles = p.tiles_m * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PS; ++s) { mbar_init(&x_full[s], 1); mbar_init(&p_ready[s], GNC_TRANSFORM_WARPS); mbar_init(&p_empty[s], 1); }
+        for (int s = 0; s < WS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    SGAM_PDL_WAIT();
+
+    if (warp == 0) {
+        // ===== TMA producer: fp32 pixel rows (one stage per filter row and channel chunk), three weight tiles behind each =====
+        if (lane == 0) {
+            const bool three = p.nsplit == 3;
+            int pc = 0, wc = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.tiles_n) * 128;
+                int t = tile / p.tiles_n;
+                const int tx = t % g.tiles_x2; t /= g.tiles_x2;
+                const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
+                const int cx = tx * BWT - 1;
+                for (int kh = 0; kh < 3; ++kh) {
+                    for (int kc = 0; kc < KC; ++kc, ++pc) {
+                        const int ps = pc % PS;
+                        mbar_wait(&p_empty[ps], ((pc / PS) & 1) ^ 1);
+                        uint8_t *pst = p_ring + (size_t)ps * P_STAGE;
+                        mbar_expect_tx(&x_full[ps], X_TX);
+                        tma_load_4d(pst, &mapX, &x_full[ps], kc * 64, cx, ty + kh - 1, b);
+                        tma_load_4d(pst + BWT * 256, &mapXT, &x_full[ps], kc * 64, cx + BWT, ty + kh - 1, b);
+                        for (int kw = 0; kw < 3; ++kw, ++wc) {
+                            const int ws = wc % WS;
+                            mbar_wait(&w_empty[ws], ((wc / WS) & 1) ^ 1);
+                            uint8_t *wst = w_ring + (size_t)ws * W_STAGE;
+                            const int kcol = (kh * 3 + kw) * Cin + kc * 64;
+                            mbar_expect_tx(&w_full[ws], three ? W_STAGE : W_PLANE);
+                            tma_load_3d(wst, &mapW_hi, &w_full[ws], kcol, n0, 0);
+                            if (three) tma_load_3d(wst + W_PLANE, &mapW_lo, &w_full[ws], kcol, n0, 0);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (as tc_gemm_swaprow_kernel<1>, but a pixel stage is ready when the transform warps have written it) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BWT);
+            const bool three = p.nsplit == 3;
+            int pc = 0, wc = 0, li = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+                const int acc = li & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((li >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                for (int kh = 0; kh < 3; ++kh) {
+                    for (int kc = 0; kc < KC; ++kc, ++pc) {
+                        const int ps = pc % PS;
+                        mbar_wait(&p_ready[ps], (pc / PS) & 1);
+                        tc_fence_after();
+                        const uint8_t *pst = p_ring + (size_t)ps * P_STAGE;
+                        for (int kw = 0; kw < 3; ++kw, ++wc) {
+                            const int ws = wc % WS;
+                            mbar_wait(&w_full[ws], (wc / WS) & 1);
+                            tc_fence_after();
+                            const uint8_t *wst = w_ring + (size_t)ws * W_STAGE;
+                            const uint64_t w_hi = make_smem_desc<128>(wst), w_lo = make_smem_desc<128>(wst + W_PLANE);
+                            const uint64_t a_hi = make_smem_desc<128>(pst + kw * 128), a_lo = make_smem_desc<128>(pst + P_PLANE + kw * 128);
+                            const uint32_t fresh = (kh | kc | kw) ? 1u : 0u;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t off = (uint64_t)(k * 2);
+                                umma_bf16(tmem_d, w_hi + off, a_hi + off, idesc, (fresh | (uint32_t)k) ? 1u : 0u);
+                                if (three) {
+                                    umma_bf16(tmem_d, w_hi + off, a_lo + off, idesc, 1u);
+                                    umma_bf16(tmem_d, w_lo + off, a_hi + off, idesc, 1u);
+                                }
+                            }
+                            umma_commit(&w_empty[ws]);
+                        }
+                        umma_commit(&p_empty[ps]);
+                    }
+                }
+                umma_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else if (warp < 6) {
+        const int q = warp & 3;
+        int li = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+            const int acc = li & 1;
+            const int n0 = (tile % p.tiles_n) * 128;
+            int t = tile / p.tiles_n;
+            const int tx = t % g.tiles_x2; t /= g.tiles_x2;
+            const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
+            mbar_wait(&tmem_full_bar[acc], (li >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+            swap_epilogue_tile(p, g, tmem_acc, q, lane, n0, tx, ty, b);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+    } else {
+        // ===== transform warps: fp32 rows -> GroupNorm + swish -> split-bf16 planes, in place =====
+        const int tt = threadIdx.x - TC_THREADS;                    // 0 .. 255
+        const int quad = tt & 15;                                   // this thread's channel quad inside the 64-channel chunk
+        constexpr int NQ = (BWT + 2) * 16;                          // float4 elements per stage
+        constexpr int PER = (NQ + 255) / 256;                       // 17
+        int pc = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int t = tile / p.tiles_n;
+            const int tx = t % g.tiles_x2; t /= g.tiles_x2;
+            const int ty = t % g.tiles_y2; const int b = t / g.tiles_y2;
+            const int cx = tx * BWT - 1;
+            for (int kh = 0; kh < 3; ++kh) {
+                const int cy = ty + kh - 1;
+                const bool row_in = cy >= 0 && cy < gn.H;
+                for (int kc = 0; kc < KC; ++kc, ++pc) {
+                    const int ps = pc % PS;
+                    const int c0 = kc * 64 + quad * 4;
+                    const int grp = c0 / gn.cpg;
+                    const float mu = __ldg(gn.meanrstd + (b * 32 + grp) * 2), rs = __ldg(gn.meanrstd + (b * 32 + grp) * 2 + 1);
+                    const float4 ga = __ldg(reinterpret_cast<const float4 *>(gn.gamma + c0)), be = __ldg(reinterpret_cast<const float4 *>(gn.beta + c0));
+                    uint8_t *pst = p_ring + (size_t)ps * P_STAGE;
+                    mbar_wait(&x_full[ps], (pc / PS) & 1);          // (one poller per warp + __syncwarp measured slower)
+                    uint2 hi[PER], lo[PER];
+#pragma unroll
+                    for (int j = 0; j < PER; ++j) {
+                        const int i = tt + 256 * j;                 // float4 index: pixel i / 16, quad i % 16 (= quad)
+                        if (i < NQ) {
+                            const int px = i >> 4;
+                            const float4 v = *reinterpret_cast<const float4 *>(pst + (size_t)i * 16);
+                            float o[4] = {(v.x - mu) * rs * ga.x + be.x, (v.y - mu) * rs * ga.y + be.y,
+                                          (v.z - mu) * rs * ga.z + be.z, (v.w - mu) * rs * ga.w + be.w};
+                            if (gn.probe == 2) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+                            if (gn.probe == 0) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) o[k] = __fdividef(o[k], 1.0f + __expf(-o[k]));
+                            }
+                            const int gx = cx + px;
+                            if (!(row_in && gx >= 0 && gx < gn.W)) { o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; }
+                            split2(o[0], o[1], hi[j].x, lo[j].x);
+                            split2(o[2], o[3], hi[j].y, lo[j].y);
+                        }
+                    }
+                    asm volatile("bar.sync 2, 256;" ::: "memory");         // every fp32 value of the stage is in registers
+#pragma unroll
+                    for (int j = 0; j < PER; ++j) {
+                        const int i = tt + 256 * j;
+                        if (i < NQ) {
+                            const int px = i >> 4;
+                            // K-major SWIZZLE_128B row px: 16-byte chunk (quad / 2) ^ (row & 7), 8 bytes at (quad & 1) * 8
+                            const uint32_t off = (uint32_t)px * 128u + ((((uint32_t)quad >> 1) ^ ((uint32_t)px & 7u)) << 4) + (((uint32_t)quad & 1u) << 3);
+                            *reinterpret_cast<uint2 *>(pst + off) = hi[j];
+                            *reinterpret_cast<uint2 *>(pst + P_PLANE + off) = lo[j];
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_ready[ps]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+int gnconv_mode() {            // SGAM_TC_GNCONV=0: GroupNorm apply as a separate pass everywhere
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SGAM_TC_GNCONV"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
 int swap_mode() {              // 0 = off, 64 = BK 64 / 2 stages, 32 = BK 32 / 4 stages (SGAM_TC_SWAP)
     static int v = -1;
     if (v < 0) { const char *e = getenv("SGAM_TC_SWAP"); v = e ? atoi(e) : 64; if (v != 0 && v != 32 && v != 64) v = 64; }
@@ -487,6 +710,45 @@ int launch_conv_swap(const void *x_hi, const void *x_lo, const void *w_hi, const
     }
     if (BK == 32) return launch_swap<32, 4>(p_hi, p_lo, wm_hi, wm_lo, p, g, s);
     return launch_swap<64, 2>(p_hi, p_lo, wm_hi, wm_lo, p, g, s);
+}
+
+// Does the fused GroupNorm + conv kernel apply?  A plain 3x3 / stride-1 conv the swapped-operand row kernel takes, one image row per
+// tile (W % 256 == 0), channel groups that are whole channel quads.
+bool gnconv_applicable(int B, int H, int W, int Cin, int Cout) {
+    return gnconv_mode() && swaprow_mode() && W % 256 == 0 && Cin % 64 == 0 && (Cin / 32) % 4 == 0 && swap_applicable(B, H, W, Cin, Cout, 1, true);
+}
+
+int launch_gnconv(const float *x, const float *meanrstd, const float *gamma, const float *beta, const void *w_hi, const void *w_lo, TcParams p,
+                  int B, int H, int W, int Cin, int Cout, cudaStream_t s) {
+    SwapGeom g;
+    g.BW2 = 256; g.BH2 = 1; g.tiles_x2 = W / 256; g.tiles_y2 = H;
+    g.wide = 1; g.tiles128_x = W / 128;
+    g.tiles128 = cdiv(W, 128) * H;
+    CUtensorMap mx, mxt, wm_hi, wm_lo;
+    const long long adims[4] = {Cin, W, H, B};
+    const int abox[4] = {64, 256, 1, 1}, tbox[4] = {64, 2, 1, 1};
+    const long long bdims[3] = {9LL * Cin, Cout, 1};
+    const int wbox[3] = {64, 128, 1};
+    int rc;
+    if ((rc = make_map_f32(&mx, x, 4, adims, abox)) || (rc = make_map_f32(&mxt, x, 4, adims, tbox)) ||
+        (rc = make_map(&wm_hi, w_hi, 3, bdims, wbox)) || (rc = make_map(&wm_lo, w_lo, 3, bdims, wbox)))
+        return rc;
+    p.kblocks_per_tap = Cin / 64;
+    p.tiles_m = g.tiles_x2 * g.tiles_y2 * B;
+    p.tiles_n = Cout / 128;
+    p.ksplit = 1;
+    static int probe = -1;
+    if (probe < 0) { const char *e = getenv("SGAM_GNCONV_PROBE"); probe = e ? atoi(e) : 0; }
+    GnOperand gn{meanrstd, gamma, beta, Cin / 32, H, W, probe};
+    static bool configured = false;
+    if (!configured) {
+        SGAM_CUDA_OK(cudaFuncSetAttribute(tc_gemm_gnconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RowCfg<1>::SMEM));
+        configured = true;
+    }
+    const int total = p.tiles_m * p.tiles_n;
+    const int grid = total < sm_count_cached() ? total : sm_count_cached();
+    SGAM_PDL_LAUNCH(SGAM_PDL_GEMM1, tc_gemm_gnconv_kernel, grid, GNC_THREADS, RowCfg<1>::SMEM, s, mx, mxt, wm_hi, wm_lo, p, g, Cin, gn);
+    return SGAM_OK;
 }
 
 }  // namespace tc

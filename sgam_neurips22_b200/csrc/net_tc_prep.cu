@@ -561,6 +561,17 @@ extern "C" int sgam_groupnorm_split_fused(const float *x, const float *gamma, co
     return SGAM_OK;
 }
 
+// mean / rstd of every (image, group) from the per-pixel-block sums a conv epilogue left in gn_partial (layout of
+// sgam_tc_gn_partial_floats: the [B][32][2] result goes behind the partial sums); used by the fused GroupNorm + conv kernel (net_tc3.cu)
+int sgam_gn_finalize_launch(float *gn_partial, int B, int H, int W, int C, cudaStream_t s, float **meanrstd_out) {
+    const int BW = W >= 128 ? 128 : W, BH = 128 / BW;
+    const int tiles = cdiv(W, BW) * cdiv(H, BH);
+    float *meanrstd = gn_partial + (long long)B * tiles * 64;
+    SGAM_PDL_LAUNCH(SGAM_PDL_NORM, gn_finalize_kernel, cdiv(B * 32, 8), 256, 0, s, gn_partial, meanrstd, tiles, (double)H * W * (C / 32), B * 32);
+    *meanrstd_out = meanrstd;
+    return SGAM_OK;
+}
+
 extern "C" int sgam_softmax_split(const float *x, void *hi, void *lo, long long rows, int cols, void *stream) {
     SGAM_REQUIRE(x && hi && lo && rows > 0 && cols > 0 && cols % 8 == 0, "softmax_split: cols must be a multiple of 8");
     cudaStream_t s = (cudaStream_t)stream;

@@ -530,6 +530,37 @@ def attention_tc(q, k, vT, scale, kv_splits=None):
     return o
 
 
+def gn_conv2d_tc_supported(B, H, W, Cin, Cout):
+    return bool(_lib.load().sgam_gn_conv2d_tc_supported(B, H, W, Cin, Cout))
+
+
+def gn_conv2d_tc(x, gamma, beta, w, bias, residual=None, out_f32=True, out_split=False, nsplit=3, gn_stats=True):
+    """GroupNorm + swish + 3x3 conv in one tcgen05 kernel (the normalisation runs inside the conv's operand path).  x fp32 NHWC
+    [B,H,W,Cin] carrying the partial sums of its producer (`x.gn_partial`); w = (hi, lo) [Cout, 9*Cin]; returns like conv2d_tc."""
+    lib = _lib.load()
+    _chk(x, name="x"), _chk(gamma, name="gamma"), _chk(beta, name="beta"), _chk(w[0], torch.bfloat16, "w_hi"), _chk(w[1], torch.bfloat16, "w_lo")
+    partial_in = getattr(x, "gn_partial", None)
+    if partial_in is None:
+        raise RuntimeError("gn_conv2d_tc: x carries no fused GroupNorm statistics (gn_partial)")
+    B, H, W, Cin = x.shape
+    Cout = w[0].shape[0]
+    if w[0].shape[1] != 9 * Cin:
+        raise RuntimeError(f"gn_conv2d_tc: weight {tuple(w[0].shape)} does not match Cin={Cin}")
+    if residual is not None:
+        _chk(residual, name="residual")
+    y = torch.empty(B, H, W, Cout, device=x.device) if out_f32 else None
+    pair = _bf16_pair((B, H, W, Cout), x.device) if out_split else (None, None)
+    partial = torch.empty(lib.sgam_tc_gn_partial_floats(B, H, W), device=x.device) if (gn_stats and out_f32 and Cout % 128 == 0 and Cout <= 512) else None
+    _lib.check(lib.sgam_gn_conv2d_tc(x.data_ptr(), partial_in.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w[0].data_ptr(), w[1].data_ptr(),
+                                     _ptr(bias), _ptr(residual), _ptr(y), _ptr(pair[0]), _ptr(pair[1]), B, H, W, Cin, Cout, int(nsplit),
+                                     _ptr(partial), _stream()), "sgam_gn_conv2d_tc")
+    if partial is not None:
+        y.gn_partial = partial
+    if out_f32 and out_split:
+        return y, pair
+    return y if out_f32 else pair
+
+
 def qkv_tc_supported(B, H, W, C):
     return bool(_lib.load().sgam_qkv_tc_supported(B, H, W, C))
 

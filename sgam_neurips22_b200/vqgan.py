@@ -35,6 +35,7 @@ class VQGANEngine:
         import os
         self.fused_head = os.environ.get("SGAM_FUSED_HEAD", "1") != "0"
         self.fused_qkv = os.environ.get("SGAM_FUSED_QKV", "1") != "0"
+        self.fused_gnconv = os.environ.get("SGAM_FUSED_GNCONV", "0") == "1"   # GroupNorm apply inside the 128-channel convs: correct, slower (opt-in)
         self.emit_split = os.environ.get("SGAM_EMIT_SPLIT", "1") != "0"    # producers of Downsample / Upsample inputs write split bf16
         self.subpixel = os.environ.get("SGAM_SUBPIXEL", "1") != "0"
         self.fused_stem = os.environ.get("SGAM_FUSED_STEM", "1") != "0"
@@ -132,6 +133,13 @@ class VQGANEngine:
         tensor-core conv (Downsample / sub-pixel Upsample): return the (hi, lo) bf16 planes straight from the epilogue instead
         of an fp32 tensor that a separate pass would split (falls back to fp32 where the tensor-core path does not apply)."""
         if self.tc_ok(conv_name, x.shape, 3):
+            B, H, W, Cin = x.shape
+            if self.fused_gnconv and getattr(x, "gn_partial", None) is not None and \
+                    ops.gn_conv2d_tc_supported(B, H, W, Cin, self.p[f"{conv_name}.weight"].shape[0]):
+                # 128-channel layers on wide images: GroupNorm + swish + split run inside the conv's operand path
+                return ops.gn_conv2d_tc(x, self.p[f"{norm_name}.weight"], self.p[f"{norm_name}.bias"], self.wsplit[conv_name],
+                                        self.p[f"{conv_name}.bias"], residual=residual, out_f32=not want_split, out_split=want_split,
+                                        nsplit=self.nsplit)
             if want_split and self.unsplit_k(conv_name, x.shape, 3):
                 return self.conv_tc(conv_name, self.norm_split(norm_name, x, True), 3, residual=residual, out_f32=False, out_split=True)
             return self.conv_tc(conv_name, self.norm_split(norm_name, x, True), 3, residual=residual)

@@ -384,3 +384,41 @@ def test_swapped_kernel_emits_split_planes(ops, B, H, W, C, res):
     assert torch.equal(y, y2)
     for got in (pair, only):
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+
+
+@pytest.mark.parametrize("B,H,W,res,want_split", [(1, 256, 256, True, False), (2, 128, 256, False, False), (1, 152, 512, True, True)])
+def test_fused_groupnorm_conv_matches_the_two_kernel_path(ops, B, H, W, res, want_split):
+    """GroupNorm + swish + split inside the conv's operand path (sgam_gn_conv2d_tc) against GroupNorm-apply followed by the conv:
+    the same operand bits, so the same result bits -- and both within 5e-5 of the fp64 reference (diffusionmodules/model.py:117-131)."""
+    C = 128
+    if not ops.gn_conv2d_tc_supported(B, H, W, C, C):
+        pytest.skip("shape not routed to the fused kernel")
+    g = torch.Generator().manual_seed(H + W)
+    x0 = torch.randn(B, H, W, C, generator=g).cuda() * 2 + 0.5
+    w0 = ops.split_weight((torch.randn(C, 9 * C, generator=g) * 0.03).cuda(), pad_rows_to=32)
+    x = ops.conv2d_tc(ops.split_bf16(x0), w0, torch.zeros(C, device="cuda"), ksize=3, gn_stats=True)      # carries gn_partial
+    assert getattr(x, "gn_partial", None) is not None
+    ga, be = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    wt = (torch.randn(C, 9 * C, generator=g) * 0.03).cuda()
+    w, bias = ops.split_weight(wt, pad_rows_to=32), torch.randn(C, generator=g).cuda()
+    r = x0 if res else None
+    part = x.gn_partial.clone()
+    ref_pair = ops.groupnorm_split(x, ga, be, True)
+    kw = dict(out_f32=not want_split, out_split=want_split)
+    ref = ops.conv2d_tc(ref_pair, w, bias, residual=r, ksize=3, gn_stats=not want_split, **kw)
+    x.gn_partial = part
+    got = ops.gn_conv2d_tc(x, ga, be, w, bias, residual=r, **kw)
+    torch.cuda.synchronize()
+    if want_split:
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+        got_f = got[0].float() + got[1].float()
+    else:
+        assert torch.equal(got, ref)
+        assert torch.equal(got.gn_partial[:B * (H * W // 128) * 64], ref.gn_partial[:B * (H * W // 128) * 64])
+        got_f = got
+    xn = F.group_norm(x.permute(0, 3, 1, 2).double().cpu(), 32, ga.double().cpu(), be.double().cpu(), eps=1e-6)
+    xn = xn * torch.sigmoid(xn)
+    ref64 = F.conv2d(xn, wt.view(C, 3, 3, C).permute(0, 3, 1, 2).double().cpu(), bias.double().cpu(), padding=1)
+    if res:
+        ref64 = ref64 + x0.permute(0, 3, 1, 2).double().cpu()
+    assert rel(got_f.permute(0, 3, 1, 2), ref64) < 5e-5
